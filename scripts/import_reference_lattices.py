@@ -1,0 +1,48 @@
+"""Converts the SixTrack lattices shipped with the reference (``/root/reference/examples``)
+into this package's own serialised ``Line`` format (gzip JSON of ``Line.to_dict()``), so
+that the benchmark configurations of BASELINE.json can be rebuilt on the GPU box, where
+the reference tree does not exist.  Runs in the build container only.
+
+    python scripts/import_reference_lattices.py
+"""
+import gzip
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from xline_b200.line import Line  # noqa: E402
+from xline_b200.sixtrack_input import SixInput  # noqa: E402
+
+REF = os.environ.get("XLINE_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(ROOT, "xline_b200", "lattices")
+
+
+def convert(example, out_name, synth_fort16=False):
+    six = SixInput(os.path.join(REF, "examples", example))
+    if synth_fort16:
+        six.synthesize_fort16(seed=20261018)
+    line = Line.from_sixinput(six)
+    d = line.to_dict(keepextra=True)
+    e0 = six.initialconditions[-1] * 1e6
+    d["meta"] = dict(
+        source="examples/%s (SixTrack fort.2/fort.3/fort.8)" % example,
+        energy0_eV=e0, mass0_eV=six.pma * 1e6, harm=six.harm, tlen=six.tlen,
+        synthetic_fort16=bool(synth_fort16), n_elements=len(line),
+    )
+    fn = os.path.join(OUT, out_name + ".json.gz")
+    with gzip.GzipFile(fn, "wb", mtime=0) as fh:
+        fh.write(json.dumps(d, separators=(",", ":")).encode())
+    kinds = {}
+    for el in line.elements:
+        kinds[type(el).__name__] = kinds.get(type(el).__name__, 0) + 1
+    print(out_name, len(line), kinds, "%.1f kB" % (os.path.getsize(fn) / 1e3))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    convert("fodo", "fodo")
+    convert("lhc", "lhc", synth_fort16=True)
+    convert("bbsimple", "bbsimple")
+    convert("beambeam", "lhc_beambeam")

@@ -1,0 +1,224 @@
+"""CPU-side tests: element API, lattice packing, SixTrack reader, C-ABI surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import xline_b200 as xl
+from xline_b200 import _cabi, lattice
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_element_constructors_like_reference():
+    """reference tests/test_elements.py:4-32 and tests/test_line.py:11 (positional)."""
+    for cls in (xl.XYShift, xl.SRotation, xl.Cavity, xl.Line, xl.DipoleEdge):
+        cls()
+    assert xl.Drift(length=4).length == 4 and xl.DriftExact(length=4).length == 4
+    assert xl.Drift(0).length == 0
+    el = xl.Multipole()
+    assert el.order == 0 and el.knl[0] == 0 and el.ksl[0] == 0
+    el = xl.Multipole(knl=[1])
+    assert el.knl == [1] and el.ksl == [0] and el.order == 0
+    assert xl.Multipole(knl=[1, 2, 3]).order == 2 and xl.Multipole(ksl=[1, 2, 3]).order == 2
+    a, b = xl.Multipole(), xl.Multipole()
+    a.knl.append(3)
+    assert b.knl == [0]  # list defaults are per-instance
+    with pytest.raises(TypeError):
+        xl.Drift(foo=1)
+
+
+def test_element_dict_roundtrip_and_extra_fields():
+    bb = xl.BeamBeam4D(charge=1e11, sigma_x=1e-3, sigma_y=2e-3)
+    assert bb.min_sigma_diff == 1e-28 and bb.enabled is True
+    assert "enabled" not in bb.to_dict() and "enabled" in bb.to_dict(keepextra=True)
+    assert xl.BeamBeam4D.from_dict(bb.to_dict(keepextra=True)) == bb
+    assert bb.copy() == bb and bb.copy() is not bb
+    sc = xl.SCQGaussProfile()
+    assert sc.get_fields() == ["number_of_particles", "bunchlength_rms", "sigma_x", "sigma_y",
+                               "length", "x_co", "y_co"]
+    assert sc.q_parameter == 1.0
+
+
+def test_line_editing_and_serialisation(tmp_path):
+    line = xl.Line([xl.Drift(1.0), xl.Drift(0.0), xl.Multipole(knl=[0, 0]), xl.Drift(2.0),
+                    xl.Multipole(knl=[0, 0.1]), xl.Cavity(voltage=1e6, frequency=4e8)])
+    assert len(line) == 6 and line.get_length() == 3.0
+    assert len(line.remove_zero_length_drifts()) == 5
+    assert len(line.remove_inactive_multipoles()) == 5
+    merged = line.remove_zero_length_drifts().remove_inactive_multipoles().merge_consecutive_drifts()
+    assert len(merged) == 3 and merged.elements[0].length == 3.0
+    fn = str(tmp_path / "line.json")
+    line.to_json(fn)
+    back = xl.Line.from_json(fn)
+    assert back.to_dict() == line.to_dict()
+    assert line.get_s_elements() == [0.0, 1.0, 1.0, 1.0, 3.0, 3.0]
+
+
+def test_particles_reference_quantities():
+    """reference tests/test_particles.py:9-25."""
+    p = xl.Particles(p0c=1e9, device="cpu")
+    for setter, val in (("beta0", 0.91), ("beta0", 0.9101), ("gamma0", 1.99), ("p0c", 0.1 * p.mass0)):
+        setattr(p, setter, val)
+        err = abs(p.p0c ** 2 + p.mass0 ** 2 - p.energy0 ** 2) / p.mass0 ** 2
+        assert err < 1.2e-15
+
+
+def test_particles_loss_compaction_cpu():
+    """reference tests/test_losses.py:5-17."""
+    import torch
+
+    p = xl.Particles(p0c=1e9, x=np.arange(10, dtype=np.float64), device="cpu")
+    p.state = (p.x.to(torch.int64) % 2 == 0).to(torch.int64)
+    p.remove_lost_particles()
+    p.state = (p.x > 5).to(torch.int64)
+    p.remove_lost_particles()
+    assert p.x.tolist() == [6.0, 8.0]
+    assert [len(lp) for lp in p.lost_particles] == [5, 3]
+
+
+def test_particles_delta_setter_matches_oracle():
+    from oracle import xline_oracle as xo
+
+    d = np.linspace(-1e-3, 1e-3, 7)
+    p = xl.Particles(p0c=450e9, delta=d, device="cpu")
+    o = xo.OracleParticles(7, p0c=450e9, delta=d)
+    assert np.array_equal(p.rpp.numpy(), o.rpp) and np.array_equal(p.rvv.numpy(), o.rvv)
+
+
+def _walk(packed):
+    """Decode the packed words back into (tag, aux, element_index) triples."""
+    out = []
+    w = packed.words
+    for c in range(packed.n_chunks):
+        pos = c * packed.chunk_words
+        while True:
+            hdr = int(w[pos])
+            tag, aux, idx = hdr & 0xFF, (hdr >> 8) & 0xFFFFFF, hdr >> 32
+            if tag in (lattice.T_END_CHUNK, lattice.T_END_TURN):
+                break
+            pairs = {2: 1, 3: 1, 4: aux + 2, 5: aux + 4, 6: 2, 15: 2, 8: 2, 9: 2, 10: 2,
+                     7: 2 + 2 * (aux + 1), 11: 3, 12: 3, 13: 4, 14: 5}.get(tag)
+            if pairs is None:
+                pairs = int(w[pos + 1])
+            out.append((tag, aux, idx))
+            pos += 2 * pairs
+    return out
+
+
+def test_pack_structure_and_validation():
+    line = xl.Line([xl.Drift(1.0), xl.Drift(0.0), xl.Multipole(knl=[0, 0.1, 3.0], ksl=[0, 0, 0, 6.0]),
+                    xl.Multipole(knl=[1e-3], hxl=1e-3, length=2.0), xl.LimitRect(), xl.Cavity(voltage=1.0),
+                    xl.RFMultipole(knl=[1, 2]), xl.SRotation(angle=3), xl.XYShift(dx=1),
+                    xl.DipoleEdge(h=1), xl.LimitEllipse(), xl.LimitRectEllipse(), xl.DriftExact(1.0),
+                    xl.BeamMonitor(num_stores=2, max_particle_id=9)])
+    pk = line.pack()
+    recs = _walk(pk)
+    assert [r[2] for r in recs] == [0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]  # zero drift dropped
+    assert recs[1][:2] == (lattice.T_MULTIPOLE, 3)
+    assert recs[2][0] == lattice.T_MULTIPOLE_CURVED
+    assert pk.monitor_words == 7 * 2 * 10
+    # fast encoding folds 1/i!
+    w = pk.words.view(np.float64)
+    base = 2  # after the drift record
+    assert w[base + 2] == 0.0 and w[base + 3] == 6.0 / 6.0
+    assert w[base + 4] == 3.0 / 2.0
+    ws = line.pack(strict=True).words.view(np.float64)
+    assert ws[base + 3] == 6.0 and ws[base + 4] == 3.0
+    assert line.pack(strict=True).flags & lattice.F_STRICT
+    # corrupt a header: the C-side validator must reject it
+    bad = pk.words.copy()
+    bad[0] = np.uint64(77)
+    lat = _cabi.Lattice(bad.ctypes.data, bad.size, pk.chunk_words, pk.n_chunks, pk.n_elements, pk.flags)
+    assert _cabi.lib().xlb_lattice_validate(C.byref(lat)) != 0
+    assert b"unknown tag" in _cabi.lib().xlb_last_error()
+
+
+def test_pack_chunking_never_splits_a_record():
+    els = []
+    for i in range(3000):
+        els += [xl.Drift(1.0 + i), xl.Multipole(knl=list(range(1, 16)), ksl=[0.0] * 15)]
+    pk = xl.Line(els).pack()
+    assert pk.n_chunks > 10
+    recs = _walk(pk)
+    assert len(recs) == 6000 and [r[2] for r in recs] == list(range(6000))
+    big = xl.SCInterpolatedProfile(number_of_particles=1.0, line_density_profile=list(np.ones(3000)),
+                                   sigma_x=1.0, sigma_y=2.0, length=1.0)
+    pk = xl.Line([xl.Drift(1.0), big]).pack()
+    assert pk.chunk_words >= 3000 and pk.flags & lattice.F_BEAMFIELDS
+
+
+def test_pack_error_behaviour():
+    with pytest.raises(ZeroDivisionError):  # gaussian_fields.py:91-92 semantics at pack time
+        xl.Line([xl.SCCoasting(number_of_particles=1.0, sigma_x=1.0, sigma_y=1.0, min_sigma_diff=0.0)]).pack()
+    xl.Line([xl.BeamBeam4D(charge=1.0, sigma_x=1.0, sigma_y=1.0)]).pack()  # round branch
+    class LimitPolygon(xl.Element):
+        _base = ()
+    with pytest.raises(NotImplementedError):
+        xl.Line([LimitPolygon()]).pack()
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "xline_b200.h")).read()
+    declared = set(re.findall(r"\b(xlb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_cabi.EXPORTS)
+    L = _cabi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.xlb_abi_version() == 1
+    # argument validation happens before any CUDA call
+    assert L.xlb_track_device(None, None, None, None) == -1
+    assert b"null" in L.xlb_last_error()
+
+
+def test_sixtrack_reader_builds_shipped_lattices():
+    from xline_b200 import configs
+
+    line, meta = configs.load_lattice("lhc")
+    kinds = {}
+    for el in line.elements:
+        kinds[type(el).__name__] = kinds.get(type(el).__name__, 0) + 1
+    # 8 316 Drift + 10 137 Multipole + 12 Cavity (+ fort.8 wrappers)
+    assert kinds["Drift"] == 8316 and kinds["Multipole"] == 10137 and kinds["Cavity"] == 12
+    assert abs(line.get_length() - meta["tlen"]) < 1e-6
+    steps = sum(el.order for el in line.elements if isinstance(el, xl.Multipole))
+    assert steps == 73394  # Horner steps per turn
+    fodo, _ = configs.load_lattice("fodo")
+    assert [type(e).__name__ for e in fodo.elements].count("Cavity") == 1
+    bb, _ = configs.load_lattice("lhc_beambeam")
+    assert sum(isinstance(e, xl.BeamBeam4D) for e in bb.elements) == 72
+    assert sum(isinstance(e, xl.BeamBeam6D) for e in bb.elements) == 2
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree absent")
+def test_sixtrack_reader_against_reference_loader():
+    """expand_struct vs the reference's own _expand_struct fed with this SixInput."""
+    from oracle import ref_harness as rh
+    from xline_b200.sixtrack_input import SixInput, expand_struct
+
+    els = rh.load_reference()
+    ref_loader = rh.reference_module("loader_sixtrack")
+    for ex in ("fodo", "lhc", "bbsimple"):
+        six = SixInput("/root/reference/examples/" + ex)
+        mine, _, iconv = expand_struct(six, xl.elements.element_classes())
+        six2 = SixInput("/root/reference/examples/" + ex)
+        theirs, _, iconv2 = ref_loader._expand_struct(six2, convert=els)
+        assert iconv == iconv2
+        assert [(n, t) for n, t, _ in mine] == [(n, t) for n, t, _ in theirs]
+        for (_, _, a), (_, _, b) in zip(mine, theirs):
+            da, db = a.to_dict(), b.to_dict()
+            for k in da:
+                if k != "__class__":
+                    assert np.array_equal(np.asarray(da[k], dtype=float), np.asarray(db[k], dtype=float)), k
+
+
+def test_algorithmic_ops_match_oracle_count():
+    from oracle import xline_oracle as xo
+    from xline_b200 import configs
+
+    line, _ = configs.load_lattice("lhc")
+    assert line.algorithmic_ops_per_turn() == xo.algorithmic_ops(line.to_specs())
+    assert abs(line.algorithmic_ops_per_turn() - 9.48e5) / 9.48e5 < 0.02

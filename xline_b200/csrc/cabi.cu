@@ -1,0 +1,626 @@
+// C ABI (include/xline_b200.h) and host-side orchestration of the tracking kernels:
+// variant selection, shared-memory ring sizing, turn segmentation with survivor
+// compaction between launches, the host-buffer entry point, and the FP64-peak probe.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xline_b200.h"
+#include "kargs.h"
+
+namespace xlb {
+const Variant *fast_bf_variants(int *n);
+const Variant *strict_bf_variants(int *n);
+
+static thread_local std::string g_err;
+static thread_local xlb_track_stats_t g_stats;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define XLB_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      return fail(XLB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    }                                                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------ survivor compaction
+// Order-preserving stream compaction of {i : state[i]==1} built from warp ballots:
+// pass 1 counts per block, pass 2 scans the block totals, pass 3 re-derives the ballots
+// and scatters.  Deterministic (no atomics on the output position).
+constexpr int CP_THREADS = 512;
+constexpr int CP_ITEMS = 8;  // elements per thread
+
+__global__ void __launch_bounds__(CP_THREADS) compact_count(const long long *state, long long n,
+                                                            int *block_sums) {
+  __shared__ int warp_cnt[CP_THREADS / 32];
+  const long long base = static_cast<long long>(blockIdx.x) * (CP_THREADS * CP_ITEMS);
+  int cnt = 0;
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    const long long i = base + static_cast<long long>(it) * CP_THREADS + threadIdx.x;
+    const bool keep = (i < n) && (state[i] == 1);
+    cnt += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) t += warp_cnt[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) compact_scan(int *block_sums, int nblocks, int *n_out) {
+  // exclusive scan of block_sums by one CTA (nblocks <= a few 1e4), warp-shuffle based
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int start = 0; start < nblocks; start += 1024) {
+    const int i = start + threadIdx.x;
+    const int v = (i < nblocks) ? block_sums[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_tot[threadIdx.x];
+      int wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (threadIdx.x >= d) wi += t;
+      }
+      warp_tot[threadIdx.x] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    const int excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+    if (i < nblocks) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = carry;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_scatter(const long long *state, long long n,
+                                                              const int *block_offs, int *idx_out) {
+  __shared__ int warp_cnt[CP_ITEMS][CP_THREADS / 32];
+  const long long base = static_cast<long long>(blockIdx.x) * (CP_THREADS * CP_ITEMS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned ballots[CP_ITEMS];
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    const long long i = base + static_cast<long long>(it) * CP_THREADS + threadIdx.x;
+    const bool keep = (i < n) && (state[i] == 1);
+    ballots[it] = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[it][warp] = __popc(ballots[it]);
+  }
+  __syncthreads();
+  // output order = increasing i: item-major, then warp, then lane
+  int off = block_offs[blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    int before = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+      const int c = warp_cnt[it][w];
+      if (w < warp) before += c;
+    }
+    int tot = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) tot += warp_cnt[it][w];
+    const long long i = base + static_cast<long long>(it) * CP_THREADS + threadIdx.x;
+    if ((ballots[it] >> lane) & 1u) {
+      const int pos = off + before + __popc(ballots[it] & ((1u << lane) - 1u));
+      idx_out[pos] = static_cast<int>(i);
+    }
+    off += tot;
+  }
+}
+
+// ------------------------------------------------------------------ per-device scratch
+struct Scratch {
+  int device = -1;
+  int *idx = nullptr;         // survivor list
+  int *block_sums = nullptr;  // compaction scratch
+  long long cap = 0;          // capacity of idx (entries)
+  int nblocks_cap = 0;
+  unsigned int *n_lost = nullptr;  // device counter
+  int *n_active = nullptr;         // device survivor count
+  unsigned int *h_pinned = nullptr;  // [0]=n_lost, [1]=n_active (pinned host)
+  // host entry point arena
+  unsigned char *arena = nullptr;
+  size_t arena_bytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static std::mutex g_mu;
+static std::vector<Scratch *> g_scratch;
+
+static int get_scratch(Scratch **out) {
+  int dev = 0;
+  XLB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Scratch *s : g_scratch)
+    if (s->device == dev) {
+      *out = s;
+      return XLB_OK;
+    }
+  Scratch *s = new Scratch();
+  s->device = dev;
+  XLB_CUDA(cudaMalloc(&s->n_lost, sizeof(unsigned int)));
+  XLB_CUDA(cudaMalloc(&s->n_active, sizeof(int)));
+  XLB_CUDA(cudaMemset(s->n_lost, 0, sizeof(unsigned int)));
+  XLB_CUDA(cudaMallocHost(&s->h_pinned, 2 * sizeof(unsigned int)));
+  XLB_CUDA(cudaEventCreate(&s->ev0));
+  XLB_CUDA(cudaEventCreate(&s->ev1));
+  g_scratch.push_back(s);
+  *out = s;
+  return XLB_OK;
+}
+
+static int ensure_compaction_scratch(Scratch *s, long long n) {
+  const int nblocks = static_cast<int>((n + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS));
+  if (n > s->cap) {
+    if (s->idx) cudaFree(s->idx);
+    s->idx = nullptr;
+    XLB_CUDA(cudaMalloc(&s->idx, static_cast<size_t>(n) * sizeof(int)));
+    s->cap = n;
+  }
+  if (nblocks > s->nblocks_cap) {
+    if (s->block_sums) cudaFree(s->block_sums);
+    s->block_sums = nullptr;
+    XLB_CUDA(cudaMalloc(&s->block_sums, static_cast<size_t>(nblocks) * sizeof(int)));
+    s->nblocks_cap = nblocks;
+  }
+  return XLB_OK;
+}
+
+static int compact_alive(const long long *state, long long n, int *idx_out, int *block_sums,
+                         int *n_out, cudaStream_t st) {
+  if (n <= 0) {
+    XLB_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int), st));
+    return XLB_OK;
+  }
+  const int nblocks = static_cast<int>((n + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS));
+  compact_count<<<nblocks, CP_THREADS, 0, st>>>(state, n, block_sums);
+  compact_scan<<<1, 1024, 0, st>>>(block_sums, nblocks, n_out);
+  compact_scatter<<<nblocks, CP_THREADS, 0, st>>>(state, n, block_sums, idx_out);
+  XLB_CUDA(cudaGetLastError());
+  return XLB_OK;
+}
+
+// ------------------------------------------------------------------ variant selection
+static const Variant *pick_variant(bool strict, bool beamfields, int ppt) {
+  int n = 0;
+  const Variant *tab;
+  if (strict)
+    tab = beamfields ? strict_bf_variants(&n) : strict_variants(&n);
+  else
+    tab = beamfields ? fast_bf_variants(&n) : fast_variants(&n);
+  const Variant *best = nullptr;
+  for (int i = 0; i < n; ++i) {
+    if (tab[i].ppt == ppt) return &tab[i];
+    if (!best || std::abs(tab[i].ppt - ppt) < std::abs(best->ppt - ppt)) best = &tab[i];
+  }
+  return best;
+}
+
+static int check_lattice_header(const xlb_lattice_t *lat) {
+  if (!lat || !lat->words) return fail(XLB_EINVAL, "lattice is null");
+  if (lat->chunk_words < 4 || (lat->chunk_words & 1))
+    return fail(XLB_ELATTICE, "chunk_words must be even and >= 4");
+  if (static_cast<long long>(lat->chunk_words) * 8 > 96 * 1024)
+    return fail(XLB_ELATTICE, "chunk larger than 96 KiB");
+  if (lat->n_chunks < 1) return fail(XLB_ELATTICE, "n_chunks < 1");
+  if (lat->n_words != static_cast<int64_t>(lat->chunk_words) * lat->n_chunks)
+    return fail(XLB_ELATTICE, "n_words != chunk_words * n_chunks");
+  if (reinterpret_cast<uintptr_t>(lat->words) & 15)
+    return fail(XLB_ELATTICE, "lattice words must be 16-byte aligned");
+  return XLB_OK;
+}
+
+static int check_particles(const xlb_particles_t *p) {
+  if (!p) return fail(XLB_EINVAL, "particles is null");
+  if (p->n < 0) return fail(XLB_EINVAL, "negative particle count");
+  if (p->n > 2147483647LL) return fail(XLB_EINVAL, "more than 2^31-1 particles per call");
+  if (p->n == 0) return XLB_OK;
+  if (!p->x || !p->px || !p->y || !p->py || !p->zeta || !p->delta || !p->rpp || !p->rvv ||
+      !p->s || !p->state || !p->at_element || !p->at_turn || !p->particle_id)
+    return fail(XLB_EINVAL, "a required particle column is null");
+  if (!(p->beta0 > 0) || !(p->energy0 > 0) || !(p->p0c > 0))
+    return fail(XLB_EINVAL, "reference particle (p0c, beta0, energy0) must be positive");
+  return XLB_OK;
+}
+
+static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
+                             const xlb_track_options_t *o, cudaStream_t st, bool timed) {
+  memset(&g_stats, 0, sizeof(g_stats));
+  int rc;
+  if ((rc = check_lattice_header(lat)) != XLB_OK) return rc;
+  if ((rc = check_particles(p)) != XLB_OK) return rc;
+  if (!o) return fail(XLB_EINVAL, "options is null");
+  if (o->num_turns < 0) return fail(XLB_EINVAL, "num_turns < 0");
+  if (p->n == 0 || o->num_turns == 0) return XLB_OK;
+
+  const bool strict = (lat->flags & XLB_F_STRICT) != 0;
+  const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
+  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread : 2;
+  const Variant *v = pick_variant(strict, beamfields, ppt_req);
+  if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
+  int threads = o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, 256);
+  if (threads % 32 || threads > v->threads)
+    return fail(XLB_EINVAL, "threads_per_block must be a multiple of 32 and <= the variant's limit");
+
+  Scratch *s = nullptr;
+  if ((rc = get_scratch(&s)) != XLB_OK) return rc;
+
+  const size_t chunk_bytes = static_cast<size_t>(lat->chunk_words) * 8;
+  const size_t smem = XLB_STAGES * chunk_bytes + 2 * XLB_STAGES * sizeof(unsigned long long);
+  XLB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  cudaFuncAttributes fa;
+  XLB_CUDA(cudaFuncGetAttributes(&fa, v->func));
+
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lat = lat->words;
+  a.chunk_words = lat->chunk_words;
+  a.n_chunks = lat->n_chunks;
+  a.x = p->x; a.px = p->px; a.y = p->y; a.py = p->py; a.zeta = p->zeta; a.delta = p->delta;
+  a.rpp = p->rpp; a.rvv = p->rvv; a.s = p->s; a.chi = p->chi; a.qr = p->charge_ratio;
+  a.state = reinterpret_cast<long long *>(p->state);
+  a.at_element = reinterpret_cast<long long *>(p->at_element);
+  a.at_turn = reinterpret_cast<long long *>(p->at_turn);
+  a.pid = reinterpret_cast<const long long *>(p->particle_id);
+  a.q0 = p->q0; a.p0c = p->p0c; a.beta0 = p->beta0; a.energy0 = p->energy0;
+  a.loss_tally = reinterpret_cast<long long *>(o->loss_tally);
+  a.mon = o->monitor_data;
+  a.mon_words = o->monitor_words;
+  a.n_lost = s->n_lost;
+
+  const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch : o->num_turns;
+  const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 16.0);
+  long long n_active = p->n;
+  const int *idx = nullptr;
+  long long lost_since_compact = 0;
+  const bool segmented = seg < o->num_turns;
+  if (segmented) XLB_CUDA(cudaMemsetAsync(s->n_lost, 0, sizeof(unsigned int), st));
+
+  if (timed) XLB_CUDA(cudaEventRecord(s->ev0, st));
+  float total_ms = 0.f;
+  for (int done = 0; done < o->num_turns && n_active > 0;) {
+    const int turns = std::min(seg, o->num_turns - done);
+    a.num_turns = turns;
+    a.n = n_active;
+    a.idx = idx;
+    const long long per_block = static_cast<long long>(threads) * v->ppt;
+    const int blocks = static_cast<int>((n_active + per_block - 1) / per_block);
+    v->launch(a, blocks, threads, smem, st);
+    XLB_CUDA(cudaGetLastError());
+    g_stats.kernel_launches += 1;
+    g_stats.blocks = blocks;
+    g_stats.threads = threads;
+    done += turns;
+    if (done >= o->num_turns) break;
+    // survivors: read the loss counter; re-compact when enough lanes went idle
+    XLB_CUDA(cudaMemcpyAsync(&s->h_pinned[0], s->n_lost, sizeof(unsigned int),
+                             cudaMemcpyDeviceToHost, st));
+    XLB_CUDA(cudaStreamSynchronize(st));
+    const long long lost_total = s->h_pinned[0];
+    const long long newly = lost_total - lost_since_compact;
+    if (newly > 0 && static_cast<double>(newly) >= thr * static_cast<double>(n_active)) {
+      if ((rc = ensure_compaction_scratch(s, p->n)) != XLB_OK) return rc;
+      if ((rc = compact_alive(a.state, p->n, s->idx, s->block_sums, s->n_active, st)) != XLB_OK)
+        return rc;
+      XLB_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      XLB_CUDA(cudaStreamSynchronize(st));
+      n_active = static_cast<int>(s->h_pinned[1]);
+      idx = s->idx;
+      lost_since_compact = lost_total;
+      g_stats.compactions += 1;
+    }
+  }
+  if (timed) {
+    XLB_CUDA(cudaEventRecord(s->ev1, st));
+    XLB_CUDA(cudaEventSynchronize(s->ev1));
+    XLB_CUDA(cudaEventElapsedTime(&total_ms, s->ev0, s->ev1));
+  }
+  g_stats.kernel_ms = total_ms;
+  g_stats.regs_per_thread = fa.numRegs;
+  g_stats.smem_bytes = static_cast<int>(smem);
+  g_stats.n_alive_in = p->n;
+  g_stats.n_alive_out = n_active;
+  return XLB_OK;
+}
+
+// ------------------------------------------------------------------ FP64 peak probe
+template <int CHAINS>
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+  double acc[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) acc[c] = threadIdx.x * 1e-3 + c;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) acc[c] = fma(acc[c], a, b);
+  }
+  double t = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) t += acc[c];
+  if (t == 123.456) out[0] = t;  // keep the chains alive
+}
+
+}  // namespace xlb
+
+using namespace xlb;
+
+extern "C" {
+
+int xlb_abi_version(void) { return XLB_ABI_VERSION; }
+const char *xlb_last_error(void) { return g_err.c_str(); }
+
+int xlb_get_stats(xlb_track_stats_t *out) {
+  if (!out) return fail(XLB_EINVAL, "out is null");
+  *out = g_stats;
+  return XLB_OK;
+}
+
+int xlb_lattice_validate(const xlb_lattice_t *lat) {
+  int rc = check_lattice_header(lat);
+  if (rc != XLB_OK) return rc;
+  bool saw_end_turn = false;
+  for (int c = 0; c < lat->n_chunks; ++c) {
+    const uint64_t *w = lat->words + static_cast<size_t>(c) * lat->chunk_words;
+    int pos = 0;
+    bool closed = false;
+    while (pos < lat->chunk_words) {
+      const uint64_t hdr = w[pos];
+      const int tag = static_cast<int>(hdr & 0xff);
+      const int aux = static_cast<int>((hdr >> 8) & 0xffffff);
+      int pairs = 0;
+      switch (tag) {
+        case XLB_T_END_TURN:
+          if (c != lat->n_chunks - 1) return fail(XLB_ELATTICE, "END_TURN before the last chunk");
+          saw_end_turn = true;
+          closed = true;
+          break;
+        case XLB_T_END_CHUNK:
+          if (c == lat->n_chunks - 1) return fail(XLB_ELATTICE, "last chunk must end with END_TURN");
+          closed = true;
+          break;
+        case XLB_T_DRIFT:
+        case XLB_T_DRIFT_EXACT: pairs = 1; break;
+        case XLB_T_MULTIPOLE: pairs = 1 + aux + 1; break;
+        case XLB_T_MULTIPOLE_CURVED: pairs = 3 + aux + 1; break;
+        case XLB_T_CAVITY:
+        case XLB_T_SAWTOOTH_CAVITY:
+        case XLB_T_XYSHIFT:
+        case XLB_T_SROTATION:
+        case XLB_T_DIPOLE_EDGE: pairs = 2; break;
+        case XLB_T_RFMULTIPOLE: pairs = 2 + 2 * (aux + 1); break;
+        case XLB_T_LIMIT_RECT:
+        case XLB_T_LIMIT_ELLIPSE: pairs = 3; break;
+        case XLB_T_LIMIT_RECT_ELLIPSE: pairs = 4; break;
+        case XLB_T_MONITOR: pairs = 5; break;
+        case XLB_T_BEAMBEAM4D:
+        case XLB_T_SPACECHARGE:
+        case XLB_T_BEAMBEAM6D: {
+          // self-describing: word 1 holds the record length in 16-byte pairs (int64)
+          if (!(lat->flags & XLB_F_BEAMFIELDS))
+            return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
+          pairs = static_cast<int>(static_cast<int64_t>(w[pos + 1]));
+          if (pairs < 2) return fail(XLB_ELATTICE, "bad beam-field record length");
+          break;
+        }
+        default: {
+          char buf[96];
+          snprintf(buf, sizeof buf, "unknown tag %d in chunk %d at word %d", tag, c, pos);
+          return fail(XLB_ELATTICE, buf);
+        }
+      }
+      if (closed) break;
+      pos += 2 * pairs;
+    }
+    if (!closed) return fail(XLB_ELATTICE, "chunk not terminated by END_CHUNK/END_TURN");
+  }
+  if (!saw_end_turn) return fail(XLB_ELATTICE, "no END_TURN record");
+  return XLB_OK;
+}
+
+int xlb_track_device(const xlb_lattice_t *lattice, xlb_particles_t *particles,
+                     const xlb_track_options_t *opts, void *stream) {
+  return track_device_impl(lattice, particles, opts, static_cast<cudaStream_t>(stream), false);
+}
+
+int xlb_track_device_timed(const xlb_lattice_t *lattice, xlb_particles_t *particles,
+                           const xlb_track_options_t *opts, void *stream) {
+  return track_device_impl(lattice, particles, opts, static_cast<cudaStream_t>(stream), true);
+}
+
+int xlb_compact_alive_device(const int64_t *state, int64_t n, int32_t *idx_out, int32_t *n_out,
+                             void *stream) {
+  if (n < 0 || (n > 0 && (!state || !idx_out)) || !n_out) return fail(XLB_EINVAL, "bad argument");
+  if (n > 2147483647LL) return fail(XLB_EINVAL, "n too large");
+  Scratch *s = nullptr;
+  int rc = get_scratch(&s);
+  if (rc != XLB_OK) return rc;
+  if ((rc = ensure_compaction_scratch(s, 1)) != XLB_OK) return rc;
+  const int nblocks = static_cast<int>((n + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS));
+  if (nblocks > s->nblocks_cap) {
+    if (s->block_sums) cudaFree(s->block_sums);
+    s->block_sums = nullptr;
+    XLB_CUDA(cudaMalloc(&s->block_sums, static_cast<size_t>(nblocks) * sizeof(int)));
+    s->nblocks_cap = nblocks;
+  }
+  return compact_alive(reinterpret_cast<const long long *>(state), n, idx_out, s->block_sums, n_out,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int xlb_track_host(const xlb_lattice_t *hl, xlb_particles_t *hp, const xlb_track_options_t *o) {
+  int rc;
+  if ((rc = check_lattice_header(hl)) != XLB_OK) return rc;
+  if ((rc = check_particles(hp)) != XLB_OK) return rc;
+  if (!o) return fail(XLB_EINVAL, "options is null");
+  if ((rc = xlb_lattice_validate(hl)) != XLB_OK) return rc;
+  const long long n = hp->n;
+  if (n == 0 || o->num_turns == 0) return XLB_OK;
+  Scratch *s = nullptr;
+  if ((rc = get_scratch(&s)) != XLB_OK) return rc;
+  if (!s->stream) XLB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  cudaStream_t st = s->stream;
+
+  // device arena: lattice | 11 fp64 columns | 4 int64 columns | tally | monitor
+  auto al = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  const size_t col = al(static_cast<size_t>(n) * 8);
+  const size_t lat_bytes = al(static_cast<size_t>(hl->n_words) * 8);
+  const size_t tally_bytes = o->loss_tally ? al(static_cast<size_t>(hl->n_elements) * 8) : 0;
+  const size_t mon_bytes = o->monitor_data ? al(static_cast<size_t>(o->monitor_words) * 8) : 0;
+  const size_t need = lat_bytes + 15 * col + tally_bytes + mon_bytes;
+  if (need > s->arena_bytes) {
+    if (s->arena) cudaFree(s->arena);
+    s->arena = nullptr;
+    s->arena_bytes = 0;
+    XLB_CUDA(cudaMalloc(&s->arena, need));
+    s->arena_bytes = need;
+  }
+  unsigned char *cur = s->arena;
+  auto take = [&](size_t bytes) { unsigned char *r = cur; cur += bytes; return r; };
+  xlb_lattice_t dl = *hl;
+  dl.words = reinterpret_cast<const uint64_t *>(take(lat_bytes));
+  XLB_CUDA(cudaMemcpyAsync(const_cast<uint64_t *>(dl.words), hl->words,
+                           static_cast<size_t>(hl->n_words) * 8, cudaMemcpyHostToDevice, st));
+  xlb_particles_t dp = *hp;
+  double **dcols[] = {&dp.x, &dp.px, &dp.y, &dp.py, &dp.zeta, &dp.delta, &dp.rpp, &dp.rvv, &dp.s};
+  double *const hcols[] = {hp->x, hp->px, hp->y, hp->py, hp->zeta, hp->delta, hp->rpp, hp->rvv, hp->s};
+  for (int c = 0; c < 9; ++c) {
+    *dcols[c] = reinterpret_cast<double *>(take(col));
+    XLB_CUDA(cudaMemcpyAsync(*dcols[c], hcols[c], static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
+  }
+  if (hp->chi) {
+    double *d = reinterpret_cast<double *>(take(col));
+    XLB_CUDA(cudaMemcpyAsync(d, hp->chi, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
+    dp.chi = d;
+  }
+  if (hp->charge_ratio) {
+    double *d = reinterpret_cast<double *>(take(col));
+    XLB_CUDA(cudaMemcpyAsync(d, hp->charge_ratio, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
+    dp.charge_ratio = d;
+  }
+  int64_t **dicols[] = {&dp.state, &dp.at_element, &dp.at_turn};
+  int64_t *const hicols[] = {hp->state, hp->at_element, hp->at_turn};
+  for (int c = 0; c < 3; ++c) {
+    *dicols[c] = reinterpret_cast<int64_t *>(take(col));
+    XLB_CUDA(cudaMemcpyAsync(*dicols[c], hicols[c], static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
+  }
+  {
+    int64_t *d = reinterpret_cast<int64_t *>(take(col));
+    XLB_CUDA(cudaMemcpyAsync(d, hp->particle_id, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
+    dp.particle_id = d;
+  }
+  xlb_track_options_t od = *o;
+  if (o->loss_tally) {
+    od.loss_tally = reinterpret_cast<int64_t *>(take(tally_bytes));
+    XLB_CUDA(cudaMemcpyAsync(od.loss_tally, o->loss_tally, static_cast<size_t>(hl->n_elements) * 8,
+                             cudaMemcpyHostToDevice, st));
+  }
+  if (o->monitor_data) {
+    od.monitor_data = reinterpret_cast<double *>(take(mon_bytes));
+    XLB_CUDA(cudaMemcpyAsync(od.monitor_data, o->monitor_data, static_cast<size_t>(o->monitor_words) * 8,
+                             cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = track_device_impl(&dl, &dp, &od, st, true)) != XLB_OK) return rc;
+  for (int c = 0; c < 9; ++c)
+    XLB_CUDA(cudaMemcpyAsync(hcols[c], *dcols[c], static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  for (int c = 0; c < 3; ++c)
+    XLB_CUDA(cudaMemcpyAsync(hicols[c], *dicols[c], static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  if (o->loss_tally)
+    XLB_CUDA(cudaMemcpyAsync(o->loss_tally, od.loss_tally, static_cast<size_t>(hl->n_elements) * 8,
+                             cudaMemcpyDeviceToHost, st));
+  if (o->monitor_data)
+    XLB_CUDA(cudaMemcpyAsync(o->monitor_data, od.monitor_data, static_cast<size_t>(o->monitor_words) * 8,
+                             cudaMemcpyDeviceToHost, st));
+  XLB_CUDA(cudaStreamSynchronize(st));
+  return XLB_OK;
+}
+
+int xlb_measure_fp64_peak(int repeats, double *flops_out, double *ms_out) {
+  if (!flops_out) return fail(XLB_EINVAL, "flops_out is null");
+  int dev = 0;
+  XLB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  XLB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  constexpr int CHAINS = 8;
+  const int iters = 1 << 15;
+  const int blocks = prop.multiProcessorCount * 8;
+  double *d = nullptr;
+  XLB_CUDA(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  XLB_CUDA(cudaEventCreate(&e0));
+  XLB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  if (repeats < 1) repeats = 1;
+  for (int r = 0; r < repeats + 2; ++r) {
+    XLB_CUDA(cudaEventRecord(e0));
+    dfma_peak_kernel<CHAINS><<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+    XLB_CUDA(cudaEventRecord(e1));
+    XLB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    XLB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 2 && ms < best) best = ms;  // first two are warm-up
+  }
+  XLB_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = 2.0 * CHAINS * static_cast<double>(iters) * 256.0 * blocks;
+  *flops_out = flops / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return XLB_OK;
+}
+
+int xlb_kernel_variant_count(void) {
+  int a = 0, b = 0, c = 0, d = 0;
+  fast_variants(&a);
+  strict_variants(&b);
+  fast_bf_variants(&c);
+  strict_bf_variants(&d);
+  return a + b + c + d;
+}
+
+int xlb_kernel_variant_info(int i, char *name, int name_len, int *regs, int *max_threads) {
+  int n[4];
+  const Variant *t[4] = {fast_variants(&n[0]), strict_variants(&n[1]), fast_bf_variants(&n[2]),
+                         strict_bf_variants(&n[3])};
+  for (int k = 0; k < 4; ++k) {
+    if (i < n[k]) {
+      const Variant &v = t[k][i];
+      if (name && name_len > 0) {
+        strncpy(name, v.name, name_len - 1);
+        name[name_len - 1] = 0;
+      }
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, v.func);
+      if (regs) *regs = (e == cudaSuccess) ? fa.numRegs : -1;
+      if (max_threads) *max_threads = v.threads;
+      if (e != cudaSuccess) cudaGetLastError();
+      return XLB_OK;
+    }
+    i -= n[k];
+  }
+  return fail(XLB_EINVAL, "variant index out of range");
+}
+
+}  // extern "C"

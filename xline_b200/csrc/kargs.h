@@ -1,0 +1,39 @@
+// Kernel argument block shared by the tracking kernels and the host orchestration.
+#pragma once
+#include <stdint.h>
+
+#ifndef XLB_STAGES
+#define XLB_STAGES 3  // shared-memory ring depth for the lattice chunks
+#endif
+
+namespace xlb {
+
+struct KArgs {
+  const uint64_t *lat;  // packed lattice, device
+  int chunk_words;
+  int n_chunks;
+  int num_turns;
+  long long n;     // number of entries this launch covers (idx entries, or particles)
+  const int *idx;  // optional survivor index list (device); nullptr = identity
+  double *x, *px, *y, *py, *zeta, *delta, *rpp, *rvv, *s;
+  const double *chi, *qr;
+  long long *state, *at_element, *at_turn;
+  const long long *pid;
+  double q0, p0c, beta0, energy0;
+  long long *loss_tally;
+  double *mon;
+  long long mon_words;
+  unsigned int *n_lost;  // device counter, incremented per lost particle
+};
+
+struct Variant {
+  const char *name;
+  int strict, beamfields, ppt, threads;
+  const void *func;
+  void (*launch)(const KArgs &, int blocks, int threads, size_t smem, void *stream);
+};
+
+const Variant *fast_variants(int *n);
+const Variant *strict_variants(int *n);
+
+}  // namespace xlb

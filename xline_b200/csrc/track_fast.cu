@@ -1,0 +1,38 @@
+// Fast variants: FMA contraction on, pack-time constant folding (XLB_STRICT 0).
+#define XLB_STRICT 0
+#ifndef XLB_BEAMFIELDS
+#define XLB_BEAMFIELDS 0
+#endif
+#if XLB_BEAMFIELDS
+#define XLB_NS fast_bf
+#else
+#define XLB_NS fast_lean
+#endif
+#include "track_impl.cuh"
+#include "variants.inc"
+
+namespace xlb {
+using namespace XLB_NS;
+XLB_DEF_VARIANT(1, 512, 2)
+XLB_DEF_VARIANT(2, 256, 2)
+XLB_DEF_VARIANT(4, 128, 2)
+
+#if XLB_BEAMFIELDS
+#define XLB_TABLE fast_bf_table
+#define XLB_TABLE_FN fast_bf_variants
+#define XLB_SUFFIX "/beamfields"
+#else
+#define XLB_TABLE fast_table
+#define XLB_TABLE_FN fast_variants
+#define XLB_SUFFIX "/lean"
+#endif
+static const Variant XLB_TABLE[] = {
+    XLB_VARIANT_ENTRY("fast/ppt1" XLB_SUFFIX, 1, 512, 2),
+    XLB_VARIANT_ENTRY("fast/ppt2" XLB_SUFFIX, 2, 256, 2),
+    XLB_VARIANT_ENTRY("fast/ppt4" XLB_SUFFIX, 4, 128, 2),
+};
+const Variant *XLB_TABLE_FN(int *n) {
+  *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));
+  return XLB_TABLE;
+}
+}  // namespace xlb

@@ -1,0 +1,443 @@
+"""Packs a list of elements into the flat device lattice buffer of
+``include/xline_b200.h`` (element type tags + fp64 parameters, cut into TMA-sized chunks).
+
+Everything that depends only on element fields is evaluated here, once, on the host:
+``2*pi*f/c`` and ``lag*pi/180`` of cavities (``xline/elements.py:241-243``), ``cos/sin`` of
+``SRotation`` (``:380-382``), the ``DipoleEdge`` matrix entries (``:542-546``), the
+Bassetti-Erskine prefactors (``be_beamfields/gaussian_fields.py:49-50``), the whole of
+``BB6D_init`` (``be_beamfields/BB6Ddata.py:192-304``, which the reference redoes on every
+``track`` call).  Physical constants come from ``scipy.constants`` at run time, as in the
+reference (``xline/elements.py:2-5``) -- the kernel hard-codes none.
+
+Two encodings (see the header): ``strict=False`` folds ``1/i!`` into the multipole
+coefficients and reciprocals into aperture/curvature terms (FMA-friendly, the performance
+path); ``strict=True`` keeps raw reference parameters for the strict kernel.
+"""
+import math
+
+import numpy as np
+from scipy.constants import c as clight
+from scipy.constants import e as qe
+from scipy.constants import epsilon_0
+
+from . import elements as E
+
+T_END_TURN, T_END_CHUNK, T_DRIFT, T_DRIFT_EXACT, T_MULTIPOLE, T_MULTIPOLE_CURVED = range(6)
+T_CAVITY, T_RFMULTIPOLE, T_XYSHIFT, T_SROTATION, T_DIPOLE_EDGE = range(6, 11)
+T_LIMIT_RECT, T_LIMIT_ELLIPSE, T_LIMIT_RECT_ELLIPSE, T_MONITOR, T_SAWTOOTH_CAVITY = range(11, 16)
+T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D = 16, 17, 18
+
+F_STRICT = 1
+F_BEAMFIELDS = 2
+
+DEFAULT_CHUNK_WORDS = 2048  # 16 KiB per TMA bulk copy, 3 in flight per CTA
+MONITOR_FIELDS = ("x", "px", "y", "py", "zeta", "delta", "at_turn")
+
+_FACT = [math.factorial(i) for i in range(64)]
+
+
+def _f2u(x):
+    return np.array([x], dtype=np.float64).view(np.uint64)[0]
+
+
+def _i2u(i):
+    return np.array([i], dtype=np.int64).view(np.uint64)[0]
+
+
+def _hdr(tag, aux, idx):
+    assert 0 <= tag < 256 and 0 <= aux < (1 << 24) and 0 <= idx < (1 << 31)
+    return np.uint64(tag | (aux << 8) | (idx << 32))
+
+
+class _Rec:
+    """One record under construction: header word + fp64/int64 words, padded to pairs."""
+
+    def __init__(self, tag, aux, idx, first=0.0):
+        self.w = [_hdr(tag, aux, idx), _f2u(first)]
+
+    def f(self, *vals):
+        self.w.extend(_f2u(float(v)) for v in vals)
+        return self
+
+    def i(self, *vals):
+        self.w.extend(_i2u(int(v)) for v in vals)
+        return self
+
+    def words(self):
+        if len(self.w) & 1:
+            self.w.append(np.uint64(0))
+        return self.w
+
+    def set_first_int(self, v):
+        self.w[1] = _i2u(v)
+
+
+def _pad(seq, size):
+    a = np.array(seq, dtype=np.float64).reshape(-1)
+    if len(a) < size:
+        a = np.concatenate([a, np.zeros(size - len(a))])
+    return a
+
+
+def _gauss_field_block(rec, sigma_x, sigma_y, min_sigma_diff):
+    """Five pairs describing a frozen 2-D Gaussian of fixed sigmas
+    (be_beamfields/gaussian_fields.py:107-121, 5-21, 29-99)."""
+    if abs(sigma_x - sigma_y) < min_sigma_diff:
+        sigma = 0.5 * (sigma_x + sigma_y)
+        rec.f(sigma_x, sigma_y).i(0, 0)
+        rec.f(1.0 / (2.0 * math.pi * epsilon_0), -0.5 / (sigma * sigma))
+        rec.f(1.0 / (2.0 * math.pi * epsilon_0 * sigma), 0.0)
+        rec.f(0.0, 0.0)
+        return
+    if sigma_x == sigma_y:
+        # gaussian_fields.py:91-92 -> 1.0/0.0 (tests/test_beamfields.py:86-98)
+        raise ZeroDivisionError("float division by zero")
+    kind = 1 if sigma_x > sigma_y else 2
+    big, small = (sigma_x, sigma_y) if kind == 1 else (sigma_y, sigma_x)
+    S = math.sqrt(2.0 * (big * big - small * small))
+    factBE = 1.0 / (2.0 * epsilon_0 * math.sqrt(math.pi) * S)
+    rec.f(sigma_x, sigma_y).i(kind, 0)
+    rec.f(factBE, 1.0 / S)
+    rec.f(small / big, big / small)
+    rec.f(1.0 / (2 * big * big), 1.0 / (2 * small * small))
+
+
+def _pack_beambeam4d(el, idx):
+    """be_beamfields/beambeam.py:45-82: min_sigma_diff hard-coded to 1e-10 (:63)."""
+    rec = _Rec(T_BEAMBEAM4D, 0, idx)
+    rec.f(el.x_bb, el.y_bb)
+    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), 1e-10)
+    rec.f(el.d_px, el.d_py)
+    rec.f(el.beta_r, float(el.charge) * qe)
+    rec.set_first_int(len(rec.words()) // 2)
+    return rec
+
+
+def _qgauss_cq(q, eps=1e-6):
+    """be_beamfields/qgauss.py:5-21."""
+    from scipy.special import gamma as tgamma
+
+    assert q < 3
+    cq = math.sqrt(math.pi)
+    if q >= (1 + eps):
+        cq *= tgamma((3 - q) / (2 * q - 2))
+        cq /= math.sqrt((q - 1)) * tgamma(1 / (q - 1))
+    elif q <= (1 - eps):
+        cq *= 2 * tgamma(1 / (1 - q))
+        cq /= (3 - q) * math.sqrt(1 - q) * tgamma((3 - q) / (2 - 2 * q))
+    return cq
+
+
+def _pack_spacecharge(el, idx):
+    """be_beamfields/spacecharge.py:26-52, 80-104, 137-177."""
+    name = type(el).__name__
+    if name == "SCCoasting":
+        kind = 0
+    elif name == "SCQGaussProfile":
+        kind = 1
+    else:
+        kind = {0: 2, 1: 3}.get(int(el.method), 0)
+    rec = _Rec(T_SPACECHARGE, kind, idx)
+    rec.f(el.x_co, el.y_co)
+    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), float(el.min_sigma_diff))
+    base = float(el.number_of_particles) * qe * float(el.length)
+    if name == "SCCoasting":
+        rec.f(base / float(el.circumference), 0.0)
+    elif name == "SCQGaussProfile":
+        q = float(el.q_parameter)
+        assert q < 3
+        assert el.bunchlength_rms > 0
+        sqrt_beta = 1 / (math.sqrt(2) * float(el.bunchlength_rms))
+        cq = _qgauss_cq(q)
+        assert abs(cq) > 0
+        gauss = not (abs(1 - q) > 1e-6)
+        rec.f(base, sqrt_beta * sqrt_beta)
+        rec.f(sqrt_beta / cq, 1.0 - q)
+        rec.f(0.0 if gauss else 1.0 / (1.0 - q), 0.0).i(1 if gauss else 0, 0)
+    else:
+        prof = np.asarray(el.line_density_profile, dtype=np.float64)
+        n = len(prof)
+        if kind == 0:  # method not in (0, 1): ld_factor = 1 (spacecharge.py:173)
+            rec.f(base, 0.0)
+        else:
+            rec.f(base, float(el.z0)).f(float(el.dz), 0.0).i(n, 0)
+            if kind == 2:
+                rec.f(*prof)
+            else:
+                from scipy.interpolate import CubicSpline
+
+                absc = np.linspace(el.z0, el.z0 + el.dz * (n - 1), n)
+                cs = CubicSpline(absc, prof)
+                # per interval: c3, c2, c1, c0 of (z - x_i) and the knot x_i
+                rec.f(*absc)
+                for k in range(4):
+                    rec.f(*cs.c[k])
+    rec.set_first_int(len(rec.words()) // 2)
+    return rec
+
+
+def _boost_scalar(x, px, y, py, sigma, delta, pb):
+    """be_beamfields/boost.py:6-49 for Python floats."""
+    sphi, cphi, tphi, salpha, calpha = pb
+    h = delta + 1.0 - math.sqrt((1.0 + delta) * (1.0 + delta) - px * px - py * py)
+    px_st = px / cphi - h * calpha * tphi / cphi
+    py_st = py / cphi - h * salpha * tphi / cphi
+    delta_st = delta - px * calpha * tphi - py * salpha * tphi + h * tphi * tphi
+    pz_st = math.sqrt((1.0 + delta_st) * (1.0 + delta_st) - px_st * px_st - py_st * py_st)
+    hx_st = px_st / pz_st
+    hy_st = py_st / pz_st
+    hsigma_st = 1.0 - (delta_st + 1) / pz_st
+    L11 = 1.0 + hx_st * calpha * sphi
+    L12 = hx_st * salpha * sphi
+    L13 = calpha * tphi
+    L21 = hy_st * calpha * sphi
+    L22 = 1.0 + hy_st * salpha * sphi
+    L23 = salpha * tphi
+    L31 = hsigma_st * calpha * sphi
+    L32 = hsigma_st * salpha * sphi
+    L33 = 1.0 / cphi
+    return (
+        L11 * x + L12 * y + L13 * sigma,
+        L21 * x + L22 * y + L23 * sigma,
+        L31 * x + L32 * y + L33 * sigma,
+    )
+
+
+def _pack_beambeam6d(el, idx):
+    """be_beamfields/beambeam.py:219-283 + BB6Ddata.py:192-304 (BB6D_init hoisted here)."""
+    z = np.atleast_1d(np.asarray(el.zeta_slices, dtype=np.float64))
+    npart = np.atleast_1d(np.asarray(el.charge_slices, dtype=np.float64))
+    assert len(z) == len(npart)
+    order = np.argsort(z)[::-1]  # head of the strong beam first (BB6Ddata.py:250-252)
+    z, npart = np.take(z, order), np.take(npart, order)
+    phi, alpha = float(el.phi), float(el.alpha)
+    pb = (math.sin(phi), math.cos(phi), math.tan(phi), math.sin(alpha), math.cos(alpha))
+    cphi = pb[1]
+    rec = _Rec(T_BEAMBEAM6D, len(z), idx)
+    rec.f(pb[0], pb[1]).f(pb[2], pb[3]).f(pb[4], 0.0)
+    # boosted Sigma matrix (BB6Ddata.py:62-75)
+    rec.f(el.sigma_11, el.sigma_12 / cphi)
+    rec.f(el.sigma_13, el.sigma_14 / cphi)
+    rec.f(el.sigma_22 / cphi / cphi, el.sigma_23 / cphi)
+    rec.f(el.sigma_24 / cphi / cphi, el.sigma_33)
+    rec.f(el.sigma_34 / cphi, el.sigma_44 / cphi / cphi)
+    rec.f(el.min_sigma_diff, el.threshold_singular)
+    rec.f(el.x_co, el.px_co).f(el.y_co, el.py_co).f(el.zeta_co, el.delta_co)
+    rec.f(el.x_bb_co, el.y_bb_co)
+    rec.f(el.d_x, el.d_px).f(el.d_y, el.d_py).f(el.d_zeta, el.d_delta)
+    rec.f(qe, 1.0 / (2.0 * math.pi * epsilon_0))
+    for zi, ni in zip(z, npart):
+        xs, ys, ss = _boost_scalar(0.0, 0.0, 0.0, 0.0, float(zi), 0.0, pb)
+        rec.f(ni, xs).f(ys, ss)
+    rec.set_first_int(len(rec.words()) // 2)
+    return rec
+
+
+def _is_noop(el, name):
+    if name in ("Drift", "DriftExact"):
+        return el.length == 0
+    if name == "Multipole":
+        return (not np.any(np.asarray(el.knl, dtype=float)) and
+                not np.any(np.asarray(el.ksl, dtype=float)) and el.hxl == 0 and el.hyl == 0)
+    if name == "XYShift":
+        return el.dx == 0 and el.dy == 0
+    if name == "SRotation":
+        return el.angle == 0
+    if name in ("BeamBeam4D", "BeamBeam6D", "SCCoasting", "SCQGaussProfile", "SCInterpolatedProfile"):
+        return not el.enabled  # `if self.enabled:` beambeam.py:46,220; spacecharge.py:27,81,138
+    return False
+
+
+def _pack_element(el, idx, strict, monitors):
+    name = type(el).__name__
+    if name == "Drift":
+        return _Rec(T_DRIFT, 0, idx, el.length)
+    if name == "DriftExact":
+        return _Rec(T_DRIFT_EXACT, 0, idx, el.length)
+    if name == "Multipole":
+        order = el.order
+        knl, ksl = _pad(el.knl, order + 1), _pad(el.ksl, order + 1)
+        curved = (el.hxl != 0 or el.hyl != 0)
+        if curved:
+            rec = _Rec(T_MULTIPOLE_CURVED, order, idx, el.hxl)
+            rec.f(el.hyl, el.length)
+            rec.f(1.0 / el.length if el.length > 0 else 0.0, 0.0)
+        else:
+            rec = _Rec(T_MULTIPOLE, order, idx)
+        for i in range(order, -1, -1):
+            if strict:
+                rec.f(knl[i], ksl[i])
+            else:
+                rec.f(knl[i] / _FACT[i], ksl[i] / _FACT[i])
+        return rec
+    if name in ("Cavity", "SawtoothCavity"):
+        tag = T_CAVITY if name == "Cavity" else T_SAWTOOTH_CAVITY
+        k = 2 * np.pi * el.frequency / clight
+        return _Rec(tag, 0, idx, el.voltage).f(k, el.lag * np.pi / 180)
+    if name == "RFMultipole":
+        order = el.order
+        deg2rad = np.pi / 180
+        k = 2 * np.pi * el.frequency / clight
+        rec = _Rec(T_RFMULTIPOLE, order, idx, el.voltage).f(k, el.lag * deg2rad)
+        knl, ksl = _pad(el.knl, order + 1), _pad(el.ksl, order + 1)
+        pn, ps = _pad(el.pn, order + 1) * deg2rad, _pad(el.ps, order + 1) * deg2rad
+        for i in range(order + 1):
+            rec.f(knl[i], ksl[i]).f(pn[i], ps[i])
+        return rec
+    if name == "XYShift":
+        return _Rec(T_XYSHIFT, 0, idx, el.dx).f(el.dy, 0.0)
+    if name == "SRotation":
+        deg2rad = np.pi / 180
+        return _Rec(T_SROTATION, 0, idx, np.cos(el.angle * deg2rad)).f(np.sin(el.angle * deg2rad), 0.0)
+    if name == "DipoleEdge":
+        corr = 2 * el.h * el.hgap * el.fint
+        r21 = el.h * np.tan(el.e1)
+        r43 = -el.h * np.tan(el.e1 - corr / np.cos(el.e1) * (1 + np.sin(el.e1) ** 2))
+        return _Rec(T_DIPOLE_EDGE, 0, idx, r21).f(r43, 0.0)
+    if name == "LimitRect":
+        return _Rec(T_LIMIT_RECT, 0, idx, el.min_x).f(el.max_x, el.min_y).f(el.max_y, 0.0)
+    if name == "LimitEllipse":
+        a2, b2 = el.a * el.a, el.b * el.b
+        return _Rec(T_LIMIT_ELLIPSE, 0, idx, a2).f(b2, 1.0 / a2).f(1.0 / b2, 0.0)
+    if name == "LimitRectEllipse":
+        a2, b2 = el.a * el.a, el.b * el.b
+        return _Rec(T_LIMIT_RECT_ELLIPSE, 0, idx, el.max_x).f(el.max_y, a2).f(b2, 1.0 / a2).f(1.0 / b2, 0.0)
+    if name == "BeamMonitor":
+        assert el.is_turn_ordered  # xline/elements.py:504
+        nn = el.max_particle_id - el.min_particle_id + 1 if el.max_particle_id >= el.min_particle_id else 0
+        off = monitors["words"]
+        slot = dict(element_index=idx, offset=off, num_stores=int(el.num_stores), nn=int(nn))
+        monitors["layout"].append(slot)
+        monitors["words"] += len(MONITOR_FIELDS) * max(int(el.num_stores), 0) * max(int(nn), 0)
+        rec = _Rec(T_MONITOR, len(monitors["layout"]) - 1, idx)
+        rec.i(el.start, max(int(el.skip), 1)).i(el.num_stores, el.min_particle_id)
+        rec.i(el.max_particle_id, 1 if el.is_rolling else 0).i(off, 0)
+        return rec
+    if name == "BeamBeam4D":
+        return _pack_beambeam4d(el, idx)
+    if name in ("SCCoasting", "SCQGaussProfile", "SCInterpolatedProfile"):
+        return _pack_spacecharge(el, idx)
+    if name == "BeamBeam6D":
+        return _pack_beambeam6d(el, idx)
+    if name == "LimitPolygon":
+        raise NotImplementedError  # xline/elements.py:483
+    raise ValueError("element type %s is not supported by the B200 tracking kernel" % name)
+
+
+class PackedLattice:
+    """Result of :func:`pack_line`: ``words`` (uint64 numpy array, chunked) + metadata."""
+
+    def __init__(self, words, chunk_words, n_chunks, n_elements, flags, monitors, counts):
+        self.words = words
+        self.chunk_words = chunk_words
+        self.n_chunks = n_chunks
+        self.n_elements = n_elements
+        self.flags = flags
+        self.monitor_layout = monitors["layout"]
+        self.monitor_words = monitors["words"]
+        self.record_counts = counts  # tag -> number of records actually packed
+
+    @property
+    def strict(self):
+        return bool(self.flags & F_STRICT)
+
+    @property
+    def nbytes(self):
+        return int(self.words.nbytes)
+
+
+def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True):
+    """Pack ``elements`` (the ``Line.elements`` list).  ``element_index`` in every record
+    is the position in that list, so ``at_element`` matches the reference's indexing even
+    though exact no-ops (zero-length drifts, all-zero multipoles, disabled lenses) are not
+    emitted."""
+    assert chunk_words % 2 == 0 and chunk_words >= 16
+    monitors = dict(layout=[], words=0)
+    recs = []
+    flags = F_STRICT if strict else 0
+    counts = {}
+    for idx, el in enumerate(elements):
+        name = type(el).__name__
+        if drop_noops and _is_noop(el, name):
+            continue
+        rec = _pack_element(el, idx, strict, monitors)
+        tag = int(rec.w[0]) & 0xFF
+        if tag in (T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D):
+            flags |= F_BEAMFIELDS
+        counts[tag] = counts.get(tag, 0) + 1
+        recs.append(rec.words())
+    biggest = max([len(r) for r in recs] + [0])
+    while biggest + 2 > chunk_words:
+        chunk_words *= 2
+    if chunk_words * 8 > 96 * 1024:
+        raise ValueError("an element record (%d words) exceeds the 96 KiB chunk limit" % biggest)
+    chunks = []
+    cur = []
+    for r in recs:
+        if len(cur) + len(r) + 2 > chunk_words:
+            cur += [_hdr(T_END_CHUNK, 0, 0), np.uint64(0)]
+            chunks.append(cur)
+            cur = []
+        cur = cur + r
+    cur += [_hdr(T_END_TURN, 0, 0), np.uint64(0)]
+    chunks.append(cur)
+    words = np.zeros(len(chunks) * chunk_words, dtype=np.uint64)
+    for i, ch in enumerate(chunks):
+        words[i * chunk_words: i * chunk_words + len(ch)] = np.array(ch, dtype=np.uint64)
+        # fill the tail with END_CHUNK/END_TURN so a stray read can never run away
+        tail = _hdr(T_END_TURN if i == len(chunks) - 1 else T_END_CHUNK, 0, 0)
+        words[i * chunk_words + len(ch): (i + 1) * chunk_words: 2] = tail
+    return PackedLattice(words, chunk_words, len(chunks), len(elements), flags, monitors, counts)
+
+
+def element_specs(elements):
+    """Neutral ``(type_name, {field: value})`` description of a line -- what the tests hand
+    to the CPU oracle (the oracle shares no code with this package)."""
+    out = []
+    for el in elements:
+        d = el.to_dict(keepextra=True)
+        d.pop("__class__")
+        d.pop("data", None)
+        out.append((type(el).__name__, d))
+    return out
+
+
+def algorithmic_ops(elements):
+    """FP64 operations per particle-turn by the SURVEY.md §8(a)/(d) convention (every
+    + - * / and **2 counts 1, each sqrt/sin/cos/exp 1, a wofz call taken as 100)."""
+    WOFZ = 100
+    total = 0
+    for el in elements:
+        name = type(el).__name__
+        if name == "Drift":
+            total += 15
+        elif name == "DriftExact":
+            total += 18
+        elif name == "Multipole":
+            total += 10 * el.order + 4 + (19 if (el.hxl != 0 or el.hyl != 0) else 0)
+        elif name in ("Cavity", "SawtoothCavity"):
+            total += 33
+        elif name == "RFMultipole":
+            total += 32 * (el.order + 1) + 38
+        elif name == "SRotation":
+            total += 12
+        elif name == "XYShift":
+            total += 2
+        elif name == "DipoleEdge":
+            total += 4
+        elif name == "LimitRect":
+            total += 4
+        elif name == "LimitEllipse":
+            total += 6
+        elif name == "LimitRectEllipse":
+            total += 10
+        elif name in ("BeamBeam4D", "SCCoasting", "SCQGaussProfile", "SCInterpolatedProfile"):
+            if el.enabled:
+                msd = 1e-10 if name == "BeamBeam4D" else el.min_sigma_diff
+                rnd = abs(el.sigma_x - el.sigma_y) < msd
+                total += 35 + (15 if rnd else 31 + 2 * WOFZ)
+        elif name == "BeamBeam6D":
+            if el.enabled:
+                ns = len(np.atleast_1d(el.charge_slices))
+                total += 200 + ns * (230 + 2 * WOFZ + 8)
+    return total

@@ -1,0 +1,284 @@
+"""``Line``: the reference's element container (``xline/line.py:24-490``) whose ``track``
+is served by the fused sm_100a kernel instead of the Python loop at
+``xline/line.py:89-95``.
+
+``Line.track(p)`` keeps the reference's signature (one pass over the elements, in place,
+returns ``None``); ``num_turns`` fuses the caller's turn loop into the same launch.
+"""
+import ctypes as C
+import json
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import elements as E
+from .lattice import MONITOR_FIELDS, algorithmic_ops, element_specs, pack_line
+
+_thick = (E.Drift, E.DriftExact)
+
+
+class Line(E.Element):
+    _base = (("elements", tuple), ("element_names", tuple))
+
+    def __init__(self, elements=(), element_names=None):
+        self.elements = list(elements)
+        if element_names is None:
+            element_names = ["e%d" % i for i in range(len(self.elements))]
+        self.element_names = list(element_names)
+        assert len(self.elements) == len(self.element_names)  # xline/line.py:38
+        self._cache = {}
+        self._monitor_buf = None
+        self.loss_tally = None
+        self.last_stats = None
+
+    def __len__(self):
+        assert len(self.elements) == len(self.element_names)
+        return len(self.elements)
+
+    # ------------------------------------------------------------------ serialisation
+    def to_dict(self, keepextra=True):
+        out = {"elements": [], "element_names": list(self.element_names)}
+        for el in self.elements:
+            d = el.to_dict(keepextra)
+            d.pop("data", None)
+            out["elements"].append(d)
+        return out
+
+    @classmethod
+    def from_dict(cls, dct, keepextra=True):
+        classes = E.element_classes()
+        els = []
+        for d in dct["elements"]:
+            kind = classes[d["__class__"]]
+            d = dict(d)
+            if kind is E.BeamMonitor:
+                d.setdefault("data", [])
+            els.append(kind.from_dict(d, keepextra))
+        return cls(elements=els, element_names=list(dct["element_names"]))
+
+    def to_json(self, filename, keepextra=True):
+        def enc(o):
+            if isinstance(o, np.ndarray):
+                return o.tolist()
+            if isinstance(o, (np.floating, np.integer, np.bool_)):
+                return o.item()
+            raise TypeError(type(o))
+
+        with open(filename, "w") as fh:
+            json.dump(self.to_dict(keepextra), fh, default=enc)
+
+    @classmethod
+    def from_json(cls, filename, keepextra=True):
+        with open(filename) as fh:
+            return cls.from_dict(json.load(fh), keepextra)
+
+    def copy(self, keepextra=True):
+        return Line.from_dict(self.to_dict(keepextra), keepextra)
+
+    # ------------------------------------------------------------------ editing (host)
+    def invalidate(self):
+        """Drop the packed-lattice cache (call after editing element fields in place)."""
+        self._cache.clear()
+        self._monitor_buf = None
+        self.loss_tally = None
+
+    def insert_element(self, idx, element, name):
+        self.elements.insert(idx, element)
+        self.element_names.insert(idx, name)
+        self.invalidate()
+        return self
+
+    def append_element(self, element, name):
+        self.elements.append(element)
+        self.element_names.append(name)
+        self.invalidate()
+        return self
+
+    def append_line(self, line):
+        self.elements += list(line.elements)
+        self.element_names += list(line.element_names)
+        self.invalidate()
+        return self
+
+    def get_length(self):  # xline/line.py:122-130
+        return sum(el.length for el in self.elements if isinstance(el, _thick))
+
+    def get_s_elements(self, mode="upstream"):  # xline/line.py:132-144
+        assert mode in ("upstream", "downstream")
+        s, out = 0.0, []
+        for el in self.elements:
+            if mode == "upstream":
+                out.append(s)
+            if isinstance(el, _thick):
+                s += el.length
+            if mode == "downstream":
+                out.append(s)
+        return out
+
+    def get_elements_of_type(self, types):
+        if not hasattr(types, "__iter__"):
+            types = (types,)
+        types = tuple(types)
+        pairs = [(el, nm) for el, nm in zip(self.elements, self.element_names) if isinstance(el, types)]
+        return [p[0] for p in pairs], [p[1] for p in pairs]
+
+    def _filtered(self, keep):
+        els, names = [], []
+        for el, nm in zip(self.elements, self.element_names):
+            if keep(el):
+                els.append(el)
+                names.append(nm)
+        return Line(els, names)
+
+    def remove_inactive_multipoles(self, inplace=False):  # xline/line.py:146-166
+        new = self._filtered(lambda el: not (isinstance(el, E.Multipole) and not np.any(el.knl)
+                                             and not np.any(el.ksl) and el.hxl == 0 and el.hyl == 0))
+        return self._adopt(new) if inplace else new
+
+    def remove_zero_length_drifts(self, inplace=False):  # xline/line.py:168-184
+        new = self._filtered(lambda el: not (isinstance(el, _thick) and el.length == 0.0))
+        return self._adopt(new) if inplace else new
+
+    def merge_consecutive_drifts(self, inplace=False):  # xline/line.py:186-211
+        els, names = [], []
+        for el, nm in zip(self.elements, self.element_names):
+            if els and type(el) is type(els[-1]) and isinstance(el, _thick):
+                els[-1] = type(el)(length=els[-1].length + el.length)
+                names[-1] = names[-1] + "_" + nm
+            else:
+                els.append(el.copy() if isinstance(el, _thick) else el)
+                names.append(nm)
+        new = Line(els, names)
+        return self._adopt(new) if inplace else new
+
+    def _adopt(self, other):
+        self.elements, self.element_names = other.elements, other.element_names
+        self.invalidate()
+        return self
+
+    # ------------------------------------------------------------------ packing
+    def to_specs(self):
+        """``[(type_name, fields), ...]`` -- neutral description (tests feed it to the oracle)."""
+        return element_specs(self.elements)
+
+    def algorithmic_ops_per_turn(self):
+        return algorithmic_ops(self.elements)
+
+    def pack(self, strict=False, chunk_words=None):
+        """Host-side packed lattice (``lattice.PackedLattice``), cached."""
+        key = ("host", bool(strict), chunk_words, tuple(map(id, self.elements)))
+        hit = self._cache.get("host_%d" % strict)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        kw = {} if chunk_words is None else {"chunk_words": chunk_words}
+        packed = pack_line(self.elements, strict=strict, **kw)
+        lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
+                            packed.n_chunks, packed.n_elements, packed.flags)
+        _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))
+        self._cache["host_%d" % strict] = (key, packed)
+        return packed
+
+    def _device_lattice(self, device, strict):
+        packed = self.pack(strict)
+        key = ("dev", str(device), bool(strict), id(packed))
+        hit = self._cache.get(key[:3])
+        if hit is not None and hit[0] == key:
+            return packed, hit[1]
+        words = torch.from_numpy(packed.words.view(np.int64)).to(device)
+        self._cache[key[:3]] = (key, words)
+        return packed, words
+
+    # ------------------------------------------------------------------ the hot path
+    def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
+              threads_per_block=0, timed=False):
+        """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
+        times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
+        returns ``None`` like the reference.
+
+        ``strict=True`` selects the reference-operation-order kernel (parity instrument).
+        ``turns_per_launch`` > 0 splits the job and re-compacts survivors between launches.
+        """
+        if p.device.type != "cuda":
+            raise RuntimeError(
+                "xline_b200.Line.track needs particles resident on a CUDA device (got %s); "
+                "there is no CPU tracking path in this package" % p.device)
+        lib = _cabi.lib()
+        with torch.cuda.device(p.device):
+            packed, words = self._device_lattice(p.device, strict)
+            n = len(p)
+            if n == 0 or num_turns == 0:
+                return None
+            lat = _cabi.Lattice(words.data_ptr(), words.numel(), packed.chunk_words, packed.n_chunks,
+                                packed.n_elements, packed.flags)
+            cols = {}
+            for k, t in p._columns():
+                if not t.is_contiguous():
+                    t = t.contiguous()
+                    p._assign(k, t)
+                cols[k] = t
+            cp = _cabi.Particles()
+            cp.n = n
+            for k, t in cols.items():
+                setattr(cp, k, t.data_ptr())
+            cp.q0, cp.mass0, cp.p0c = p.q0, p.mass0, p.p0c
+            cp.beta0, cp.gamma0, cp.energy0 = p.beta0, p.gamma0, p.energy0
+            if self.loss_tally is None or self.loss_tally.device != p.device:
+                self.loss_tally = torch.zeros(max(packed.n_elements, 1), dtype=torch.int64, device=p.device)
+            opts = _cabi.TrackOptions()
+            opts.num_turns = int(num_turns)
+            opts.particles_per_thread = int(particles_per_thread)
+            opts.threads_per_block = int(threads_per_block)
+            opts.turns_per_launch = int(turns_per_launch)
+            opts.loss_tally = self.loss_tally.data_ptr()
+            if packed.monitor_words > 0:
+                if self._monitor_buf is None or self._monitor_buf.device != p.device:
+                    self._monitor_buf = torch.full((packed.monitor_words,), float("nan"),
+                                                   dtype=torch.float64, device=p.device)
+                opts.monitor_data = self._monitor_buf.data_ptr()
+                opts.monitor_words = packed.monitor_words
+            stream = torch.cuda.current_stream(p.device).cuda_stream
+            fn = lib.xlb_track_device_timed if timed else lib.xlb_track_device
+            _cabi.check(fn(C.byref(lat), C.byref(cp), C.byref(opts), C.c_void_p(stream)))
+            self.last_stats = _cabi.stats()
+            if packed.monitor_words > 0:
+                self._publish_monitors(packed)
+        return None
+
+    def _publish_monitors(self, packed):
+        for slot in packed.monitor_layout:
+            el = self.elements[slot["element_index"]]
+            ns, nn = slot["num_stores"], slot["nn"]
+            if ns <= 0 or nn <= 0:
+                continue
+            view = self._monitor_buf[slot["offset"]: slot["offset"] + len(MONITOR_FIELDS) * ns * nn]
+            view = view.view(len(MONITOR_FIELDS), ns, nn)
+            el.data = {k: view[i] for i, k in enumerate(MONITOR_FIELDS)}
+
+    def reset_monitors(self):
+        if self._monitor_buf is not None:
+            self._monitor_buf.fill_(float("nan"))
+
+    def track_elem_by_elem(self, p, start=True, end=False):
+        """Debug path (xline/line.py:97-108): one single-element launch per element,
+        returning the copies of ``p`` the reference returns."""
+        out = []
+        if start:
+            out.append(p.copy())
+        for el in self.elements:
+            Line([el], ["e"]).track(p)
+            out.append(p.copy())
+        if end:
+            out.append(p.copy())
+        return out
+
+    # ------------------------------------------------------------------ loaders
+    @classmethod
+    def from_sixinput(cls, sixinput, classes=None):
+        """xline/line.py:279-295 with this package's SixTrack reader."""
+        from .sixtrack_input import expand_struct
+
+        line_data, rest, iconv = expand_struct(sixinput, classes or E.element_classes())
+        line = cls([el for _, _, el in line_data], [nm for nm, _, _ in line_data])
+        line.other_info = {"rest": rest, "iconv": iconv}
+        return line
