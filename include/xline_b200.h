@@ -49,7 +49,8 @@ extern "C" {
  * words (chunk_words even, chunk = unit of one TMA bulk copy into shared memory).  A
  * chunk is a sequence of records; a record starts on an even word (16 B aligned):
  *
- *   word 0  header  = tag | aux << 8 | (uint64)element_index << 32
+ *   word 0  header  = tag (8 bits) | aux << 8 (8 bits) | size << 16 (16 bits, record length
+ *                     in 16-byte pairs) | (uint64)element_index << 32
  *   word 1  first fp64 parameter (or padding)
  *   word 2..        further parameters, record padded to an even number of words
  *
@@ -75,7 +76,8 @@ enum xlb_tag {
   XLB_T_XYSHIFT = 8,        /* [hdr,dx][dy,0]                    elements.py:274-276  */
   XLB_T_SROTATION = 9,      /* [hdr,cos][sin,0]                  elements.py:379-390  */
   XLB_T_DIPOLE_EDGE = 10,   /* [hdr,r21][r43,0]                  elements.py:538-548  */
-  XLB_T_LIMIT_RECT = 11,    /* [hdr,min_x][max_x,min_y][max_y,0] elements.py:401-420  */
+  XLB_T_LIMIT_RECT = 11,    /* aux=1: symmetric box (fast encoding only);
+                               [hdr,min_x][max_x,min_y][max_y,0] elements.py:401-420  */
   XLB_T_LIMIT_ELLIPSE = 12, /* [hdr,a*a][b*b,1/(a*a)][1/(b*b),0] elements.py:429-442  */
   XLB_T_LIMIT_RECT_ELLIPSE = 13, /* [hdr,max_x][max_y,a*a][b*b,1/(a*a)][1/(b*b),0]
                                                                  elements.py:453-474  */
@@ -86,8 +88,14 @@ enum xlb_tag {
   XLB_T_BEAMBEAM4D = 16,    /* see xline_b200/lattice.py         beambeam.py:45-82    */
   XLB_T_SPACECHARGE = 17,   /* aux=profile kind (0 coasting,1 q-Gaussian,2 linear
                                interp,3 cubic spline)            spacecharge.py       */
-  XLB_T_BEAMBEAM6D = 18,    /* aux=n_slices                      BB6D.py:15-155       */
-  XLB_T__COUNT = 19
+  XLB_T_BEAMBEAM6D = 18,    /* [hdr,(double)n_slices] ...        BB6D.py:15-155       */
+  XLB_T_THIN_BLOCK = 19,    /* fused thin multipole -> [aperture] -> [drift] (pack-time
+                               peephole): aux=order; [hdr,drift_length (0=none)]
+                               [i64 flags,i64 aperture_element_index] (kn_i,ks_i) i=order..0
+                               [hxl,hyl][length,1/length] if flags&1 (curved)
+                               [min_x,max_x][min_y,max_y] if flags&2 (rect; flags&8:
+                               symmetric) or [a*a,b*b][1/(a*a),1/(b*b)] if flags&4      */
+  XLB_T__COUNT = 20
 };
 
 typedef struct xlb_lattice {

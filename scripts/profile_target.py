@@ -1,0 +1,17 @@
+"""Small fixed job for ncu: LHC config (C2 lattice), one wave of particles, few turns."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import xline_b200 as xl
+from xline_b200 import configs
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 151552
+turns = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ppt = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+line, cols, p0c, m0 = configs.config_lhc(n)
+p = xl.Particles(p0c=p0c, mass0=m0, **cols)
+line.track(p, num_turns=turns, particles_per_thread=ppt, timed=True)
+torch.cuda.synchronize()
+print(line.last_stats, int((p.state == 1).sum()))

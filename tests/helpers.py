@@ -58,3 +58,18 @@ def scaled_err(a, b):
     if scale == 0:
         return float(np.max(np.abs(a[ok] - b[ok])))
     return float(np.max(np.abs(a[ok] - b[ok])) / scale)
+
+
+def floor_rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|a|, |b|, floor * rms(b)): elementwise relative error with the
+    denominator floored at ``floor`` x the beam's r.m.s. of that coordinate, so that values
+    passing through zero are judged against the coordinate's scale, not against themselves."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    ok = np.isfinite(a) & np.isfinite(b)
+    if not ok.any():
+        return 0.0
+    rms = np.sqrt(np.mean(b[ok] ** 2))
+    den = np.maximum(np.maximum(np.abs(a[ok]), np.abs(b[ok])), floor * rms)
+    den = np.where(den > 0, den, 1.0)
+    return float(np.max(np.abs(a[ok] - b[ok]) / den))

@@ -97,15 +97,11 @@ def _walk(packed):
         pos = c * packed.chunk_words
         while True:
             hdr = int(w[pos])
-            tag, aux, idx = hdr & 0xFF, (hdr >> 8) & 0xFFFFFF, hdr >> 32
+            tag, aux, size, idx = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0xFFFF, hdr >> 32
             if tag in (lattice.T_END_CHUNK, lattice.T_END_TURN):
                 break
-            pairs = {2: 1, 3: 1, 4: aux + 2, 5: aux + 4, 6: 2, 15: 2, 8: 2, 9: 2, 10: 2,
-                     7: 2 + 2 * (aux + 1), 11: 3, 12: 3, 13: 4, 14: 5}.get(tag)
-            if pairs is None:
-                pairs = int(w[pos + 1])
             out.append((tag, aux, idx))
-            pos += 2 * pairs
+            pos += 2 * size
     return out
 
 
@@ -115,6 +111,7 @@ def test_pack_structure_and_validation():
                     xl.RFMultipole(knl=[1, 2]), xl.SRotation(angle=3), xl.XYShift(dx=1),
                     xl.DipoleEdge(h=1), xl.LimitEllipse(), xl.LimitRectEllipse(), xl.DriftExact(1.0),
                     xl.BeamMonitor(num_stores=2, max_particle_id=9)])
+    line.fuse_records = False
     pk = line.pack()
     recs = _walk(pk)
     assert [r[2] for r in recs] == [0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]  # zero drift dropped
@@ -137,6 +134,26 @@ def test_pack_structure_and_validation():
     assert b"unknown tag" in _cabi.lib().xlb_last_error()
 
 
+def test_pack_fuses_multipole_aperture_drift():
+    line = xl.Line([xl.Multipole(knl=[0, 0.1]), xl.LimitEllipse(a=1, b=2), xl.Drift(3.0),
+                    xl.Multipole(knl=[1e-3], hxl=1e-3, length=2.0), xl.Drift(0.0), xl.Drift(4.0),
+                    xl.LimitRect(), xl.Multipole(knl=[0, 0, 1]), xl.LimitRect(min_x=-2, max_x=1)])
+    pk = line.pack()
+    recs = _walk(pk)
+    T = lattice.T_THIN_BLOCK
+    assert [(r[0], r[2]) for r in recs] == [(T, 0), (T, 3), (lattice.T_LIMIT_RECT, 6), (T, 7)]
+    w = pk.words
+    f = pk.words.view(np.float64)
+    assert f[1] == 3.0 and int(w[2]) == lattice.TB_ELLIPSE and int(w[3]) == 1
+    size0 = (int(w[0]) >> 16) & 0xFFFF
+    second = 2 * size0
+    assert f[second + 1] == 4.0 and int(w[second + 2]) == lattice.TB_CURVED
+    third = second + 2 * ((int(w[second]) >> 16) & 0xFFFF)
+    assert (int(w[third + 8 - 8]) >> 8) & 0xFF == 1  # symmetric rect flagged in aux
+    line.fuse_records = False
+    assert len(_walk(line.pack())) == 8
+
+
 def test_pack_chunking_never_splits_a_record():
     els = []
     for i in range(3000):
@@ -144,7 +161,8 @@ def test_pack_chunking_never_splits_a_record():
     pk = xl.Line(els).pack()
     assert pk.n_chunks > 10
     recs = _walk(pk)
-    assert len(recs) == 6000 and [r[2] for r in recs] == list(range(6000))
+    # leading drift, then (multipole -> drift) pairs fused, last multipole alone
+    assert len(recs) == 3001 and [r[2] for r in recs] == [0] + list(range(1, 6000, 2))
     big = xl.SCInterpolatedProfile(number_of_particles=1.0, line_density_profile=list(np.ones(3000)),
                                    sigma_x=1.0, sigma_y=2.0, length=1.0)
     pk = xl.Line([xl.Drift(1.0), big]).pack()

@@ -204,7 +204,9 @@ static int compact_alive(const long long *state, long long n, int *idx_out, int 
 }
 
 // ------------------------------------------------------------------ variant selection
-static const Variant *pick_variant(bool strict, bool beamfields, int ppt) {
+// Among the variants of the requested particles-per-thread, the one with the smallest
+// launch-bounds ceiling that still admits `threads` (tighter ceilings allow more registers).
+static const Variant *pick_variant(bool strict, bool beamfields, int ppt, int threads) {
   int n = 0;
   const Variant *tab;
   if (strict)
@@ -213,8 +215,14 @@ static const Variant *pick_variant(bool strict, bool beamfields, int ppt) {
     tab = beamfields ? fast_bf_variants(&n) : fast_variants(&n);
   const Variant *best = nullptr;
   for (int i = 0; i < n; ++i) {
-    if (tab[i].ppt == ppt) return &tab[i];
-    if (!best || std::abs(tab[i].ppt - ppt) < std::abs(best->ppt - ppt)) best = &tab[i];
+    const Variant &v = tab[i];
+    if (!best) { best = &v; continue; }
+    const int dv = std::abs(v.ppt - ppt), db = std::abs(best->ppt - ppt);
+    if (dv < db) { best = &v; continue; }
+    if (dv > db) continue;
+    const bool vfit = v.threads >= threads, bfit = best->threads >= threads;
+    if (vfit && (!bfit || v.threads < best->threads)) best = &v;
+    if (!vfit && !bfit && v.threads > best->threads) best = &v;
   }
   return best;
 }
@@ -259,7 +267,8 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const bool strict = (lat->flags & XLB_F_STRICT) != 0;
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
   const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread : 2;
-  const Variant *v = pick_variant(strict, beamfields, ppt_req);
+  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : 256;
+  const Variant *v = pick_variant(strict, beamfields, ppt_req, threads_req);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
   int threads = o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, 256);
   if (threads % 32 || threads > v->threads)
@@ -389,8 +398,9 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
     while (pos < lat->chunk_words) {
       const uint64_t hdr = w[pos];
       const int tag = static_cast<int>(hdr & 0xff);
-      const int aux = static_cast<int>((hdr >> 8) & 0xffffff);
-      int pairs = 0;
+      const int aux = static_cast<int>((hdr >> 8) & 0xff);
+      const int pairs = static_cast<int>((hdr >> 16) & 0xffff);
+      int want = -1;  // expected record length in pairs, -1 = variable
       switch (tag) {
         case XLB_T_END_TURN:
           if (c != lat->n_chunks - 1) return fail(XLB_ELATTICE, "END_TURN before the last chunk");
@@ -402,35 +412,45 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           closed = true;
           break;
         case XLB_T_DRIFT:
-        case XLB_T_DRIFT_EXACT: pairs = 1; break;
-        case XLB_T_MULTIPOLE: pairs = 1 + aux + 1; break;
-        case XLB_T_MULTIPOLE_CURVED: pairs = 3 + aux + 1; break;
+        case XLB_T_DRIFT_EXACT: want = 1; break;
+        case XLB_T_MULTIPOLE: want = 1 + aux + 1; break;
+        case XLB_T_MULTIPOLE_CURVED: want = 3 + aux + 1; break;
         case XLB_T_CAVITY:
         case XLB_T_SAWTOOTH_CAVITY:
         case XLB_T_XYSHIFT:
         case XLB_T_SROTATION:
-        case XLB_T_DIPOLE_EDGE: pairs = 2; break;
-        case XLB_T_RFMULTIPOLE: pairs = 2 + 2 * (aux + 1); break;
+        case XLB_T_DIPOLE_EDGE: want = 2; break;
+        case XLB_T_RFMULTIPOLE: want = 2 + 2 * (aux + 1); break;
         case XLB_T_LIMIT_RECT:
-        case XLB_T_LIMIT_ELLIPSE: pairs = 3; break;
-        case XLB_T_LIMIT_RECT_ELLIPSE: pairs = 4; break;
-        case XLB_T_MONITOR: pairs = 5; break;
-        case XLB_T_BEAMBEAM4D:
-        case XLB_T_SPACECHARGE:
-        case XLB_T_BEAMBEAM6D: {
-          // self-describing: word 1 holds the record length in 16-byte pairs (int64)
-          if (!(lat->flags & XLB_F_BEAMFIELDS))
-            return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
-          pairs = static_cast<int>(static_cast<int64_t>(w[pos + 1]));
-          if (pairs < 2) return fail(XLB_ELATTICE, "bad beam-field record length");
+        case XLB_T_LIMIT_ELLIPSE: want = 3; break;
+        case XLB_T_LIMIT_RECT_ELLIPSE: want = 4; break;
+        case XLB_T_MONITOR: want = 5; break;
+        case XLB_T_THIN_BLOCK: {
+          const int fl = static_cast<int>(static_cast<int64_t>(w[pos + 2]));
+          want = 2 + aux + 1 + ((fl & 1) ? 2 : 0) + ((fl & 6) ? 2 : 0);
           break;
         }
+        case XLB_T_BEAMBEAM4D:
+        case XLB_T_SPACECHARGE:
+        case XLB_T_BEAMBEAM6D:
+          if (!(lat->flags & XLB_F_BEAMFIELDS))
+            return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
+          if (pairs < 8) return fail(XLB_ELATTICE, "bad beam-field record length");
+          break;
         default: {
           char buf[96];
           snprintf(buf, sizeof buf, "unknown tag %d in chunk %d at word %d", tag, c, pos);
           return fail(XLB_ELATTICE, buf);
         }
       }
+      if (!closed && (pairs < 1 || (want >= 0 && pairs != want))) {
+        char buf[112];
+        snprintf(buf, sizeof buf, "record of tag %d in chunk %d at word %d has size %d, expected %d",
+                 tag, c, pos, pairs, want);
+        return fail(XLB_ELATTICE, buf);
+      }
+      if (!closed && pos + 2 * pairs + 2 > lat->chunk_words)
+        return fail(XLB_ELATTICE, "record runs past the end of its chunk");
       if (closed) break;
       pos += 2 * pairs;
     }

@@ -13,8 +13,12 @@
 
 namespace xlb {
 using namespace XLB_NS;
+XLB_DEF_VARIANT(1, 128, 5)
+XLB_DEF_VARIANT(1, 256, 3)
 XLB_DEF_VARIANT(1, 512, 2)
+XLB_DEF_VARIANT(2, 128, 3)
 XLB_DEF_VARIANT(2, 256, 2)
+XLB_DEF_VARIANT(3, 128, 2)
 XLB_DEF_VARIANT(4, 128, 2)
 
 #if XLB_BEAMFIELDS
@@ -27,9 +31,13 @@ XLB_DEF_VARIANT(4, 128, 2)
 #define XLB_SUFFIX "/lean"
 #endif
 static const Variant XLB_TABLE[] = {
-    XLB_VARIANT_ENTRY("fast/ppt1" XLB_SUFFIX, 1, 512, 2),
-    XLB_VARIANT_ENTRY("fast/ppt2" XLB_SUFFIX, 2, 256, 2),
-    XLB_VARIANT_ENTRY("fast/ppt4" XLB_SUFFIX, 4, 128, 2),
+    XLB_VARIANT_ENTRY("fast/ppt1/t128" XLB_SUFFIX, 1, 128, 5),
+    XLB_VARIANT_ENTRY("fast/ppt1/t256" XLB_SUFFIX, 1, 256, 3),
+    XLB_VARIANT_ENTRY("fast/ppt1/t512" XLB_SUFFIX, 1, 512, 2),
+    XLB_VARIANT_ENTRY("fast/ppt2/t128" XLB_SUFFIX, 2, 128, 3),
+    XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_SUFFIX, 2, 256, 2),
+    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 2),
+    XLB_VARIANT_ENTRY("fast/ppt4/t128" XLB_SUFFIX, 4, 128, 2),
 };
 const Variant *XLB_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));

@@ -44,16 +44,18 @@ def _i2u(i):
     return np.array([i], dtype=np.int64).view(np.uint64)[0]
 
 
-def _hdr(tag, aux, idx):
-    assert 0 <= tag < 256 and 0 <= aux < (1 << 24) and 0 <= idx < (1 << 31)
-    return np.uint64(tag | (aux << 8) | (idx << 32))
+def _hdr(tag, aux, idx, size_pairs=1):
+    assert 0 <= tag < 256 and 0 <= aux < 256 and 0 <= idx < (1 << 31)
+    assert 1 <= size_pairs < (1 << 16), "record too large for the 16-bit size field"
+    return np.uint64(tag | (aux << 8) | (size_pairs << 16) | (idx << 32))
 
 
 class _Rec:
     """One record under construction: header word + fp64/int64 words, padded to pairs."""
 
     def __init__(self, tag, aux, idx, first=0.0):
-        self.w = [_hdr(tag, aux, idx), _f2u(first)]
+        self.tag, self.aux, self.idx = tag, aux, idx
+        self.w = [np.uint64(0), _f2u(first)]
 
     def f(self, *vals):
         self.w.extend(_f2u(float(v)) for v in vals)
@@ -66,10 +68,8 @@ class _Rec:
     def words(self):
         if len(self.w) & 1:
             self.w.append(np.uint64(0))
+        self.w[0] = _hdr(self.tag, self.aux, self.idx, len(self.w) // 2)
         return self.w
-
-    def set_first_int(self, v):
-        self.w[1] = _i2u(v)
 
 
 def _pad(seq, size):
@@ -109,7 +109,6 @@ def _pack_beambeam4d(el, idx):
     _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), 1e-10)
     rec.f(el.d_px, el.d_py)
     rec.f(el.beta_r, float(el.charge) * qe)
-    rec.set_first_int(len(rec.words()) // 2)
     return rec
 
 
@@ -172,7 +171,6 @@ def _pack_spacecharge(el, idx):
                 rec.f(*absc)
                 for k in range(4):
                     rec.f(*cs.c[k])
-    rec.set_first_int(len(rec.words()) // 2)
     return rec
 
 
@@ -213,7 +211,7 @@ def _pack_beambeam6d(el, idx):
     phi, alpha = float(el.phi), float(el.alpha)
     pb = (math.sin(phi), math.cos(phi), math.tan(phi), math.sin(alpha), math.cos(alpha))
     cphi = pb[1]
-    rec = _Rec(T_BEAMBEAM6D, len(z), idx)
+    rec = _Rec(T_BEAMBEAM6D, 0, idx, float(len(z)))
     rec.f(pb[0], pb[1]).f(pb[2], pb[3]).f(pb[4], 0.0)
     # boosted Sigma matrix (BB6Ddata.py:62-75)
     rec.f(el.sigma_11, el.sigma_12 / cphi)
@@ -229,7 +227,6 @@ def _pack_beambeam6d(el, idx):
     for zi, ni in zip(z, npart):
         xs, ys, ss = _boost_scalar(0.0, 0.0, 0.0, 0.0, float(zi), 0.0, pb)
         rec.f(ni, xs).f(ys, ss)
-    rec.set_first_int(len(rec.words()) // 2)
     return rec
 
 
@@ -295,7 +292,8 @@ def _pack_element(el, idx, strict, monitors):
         r43 = -el.h * np.tan(el.e1 - corr / np.cos(el.e1) * (1 + np.sin(el.e1) ** 2))
         return _Rec(T_DIPOLE_EDGE, 0, idx, r21).f(r43, 0.0)
     if name == "LimitRect":
-        return _Rec(T_LIMIT_RECT, 0, idx, el.min_x).f(el.max_x, el.min_y).f(el.max_y, 0.0)
+        sym = (not strict) and el.min_x == -el.max_x and el.min_y == -el.max_y
+        return _Rec(T_LIMIT_RECT, 1 if sym else 0, idx, el.min_x).f(el.max_x, el.min_y).f(el.max_y, 0.0)
     if name == "LimitEllipse":
         a2, b2 = el.a * el.a, el.b * el.b
         return _Rec(T_LIMIT_ELLIPSE, 0, idx, a2).f(b2, 1.0 / a2).f(1.0 / b2, 0.0)
@@ -346,7 +344,46 @@ class PackedLattice:
         return int(self.words.nbytes)
 
 
-def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True):
+TB_CURVED, TB_RECT, TB_ELLIPSE, TB_RECT_SYM = 1, 2, 4, 8
+T_THIN_BLOCK = 19
+
+
+def _pack_thin_block(mp, idx, aper, drift, strict):
+    """Fused record XLB_T_THIN_BLOCK: the multipole's kick, then the aperture test, then the
+    drift -- the same maps in the same order as the three separate elements."""
+    order = mp.order
+    knl, ksl = _pad(mp.knl, order + 1), _pad(mp.ksl, order + 1)
+    flags = 0
+    aper_idx = 0
+    if mp.hxl != 0 or mp.hyl != 0:
+        flags |= TB_CURVED
+    lim = None
+    if aper is not None:
+        aper_idx, ap = aper
+        if type(ap).__name__ == "LimitRect":
+            flags |= TB_RECT
+            if (not strict) and ap.min_x == -ap.max_x and ap.min_y == -ap.max_y:
+                flags |= TB_RECT_SYM
+            lim = (ap.min_x, ap.max_x, ap.min_y, ap.max_y)
+        else:
+            flags |= TB_ELLIPSE
+            a2, b2 = ap.a * ap.a, ap.b * ap.b
+            lim = (a2, b2, 1.0 / a2, 1.0 / b2)
+    rec = _Rec(T_THIN_BLOCK, order, idx, drift[1].length if drift is not None else 0.0)
+    rec.i(flags, aper_idx)
+    for i in range(order, -1, -1):
+        if strict:
+            rec.f(knl[i], ksl[i])
+        else:
+            rec.f(knl[i] / _FACT[i], ksl[i] / _FACT[i])
+    if flags & TB_CURVED:
+        rec.f(mp.hxl, mp.hyl).f(mp.length, 1.0 / mp.length if mp.length > 0 else 0.0)
+    if lim is not None:
+        rec.f(*lim)
+    return rec
+
+
+def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True, fuse=True):
     """Pack ``elements`` (the ``Line.elements`` list).  ``element_index`` in every record
     is the position in that list, so ``at_element`` matches the reference's indexing even
     though exact no-ops (zero-length drifts, all-zero multipoles, disabled lenses) are not
@@ -356,12 +393,26 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
     recs = []
     flags = F_STRICT if strict else 0
     counts = {}
-    for idx, el in enumerate(elements):
+    live = [(idx, el) for idx, el in enumerate(elements)
+            if not (drop_noops and _is_noop(el, type(el).__name__))]
+    pos = 0
+    while pos < len(live):
+        idx, el = live[pos]
+        pos += 1
         name = type(el).__name__
-        if drop_noops and _is_noop(el, name):
-            continue
-        rec = _pack_element(el, idx, strict, monitors)
-        tag = int(rec.w[0]) & 0xFF
+        if fuse and name == "Multipole":
+            # peephole: thin multipole -> [LimitRect | LimitEllipse] -> [Drift] in one record
+            aper = drift = None
+            if pos < len(live) and type(live[pos][1]).__name__ in ("LimitRect", "LimitEllipse"):
+                aper = live[pos]
+                pos += 1
+            if pos < len(live) and type(live[pos][1]).__name__ == "Drift":
+                drift = live[pos]
+                pos += 1
+            rec = _pack_thin_block(el, idx, aper, drift, strict)
+        else:
+            rec = _pack_element(el, idx, strict, monitors)
+        tag = rec.tag
         if tag in (T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D):
             flags |= F_BEAMFIELDS
         counts[tag] = counts.get(tag, 0) + 1

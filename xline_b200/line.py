@@ -28,6 +28,7 @@ class Line(E.Element):
         self.element_names = list(element_names)
         assert len(self.elements) == len(self.element_names)  # xline/line.py:38
         self._cache = {}
+        self.fuse_records = True  # pack-time peephole: multipole -> aperture -> drift in one record
         self._monitor_buf = None
         self.loss_tally = None
         self.last_stats = None
@@ -167,12 +168,12 @@ class Line(E.Element):
 
     def pack(self, strict=False, chunk_words=None):
         """Host-side packed lattice (``lattice.PackedLattice``), cached."""
-        key = ("host", bool(strict), chunk_words, tuple(map(id, self.elements)))
+        key = ("host", bool(strict), chunk_words, self.fuse_records, tuple(map(id, self.elements)))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
         kw = {} if chunk_words is None else {"chunk_words": chunk_words}
-        packed = pack_line(self.elements, strict=strict, **kw)
+        packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records, **kw)
         lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
                             packed.n_chunks, packed.n_elements, packed.flags)
         _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))

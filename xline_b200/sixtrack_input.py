@@ -214,11 +214,12 @@ class SixInput:
             self.multblock.setdefault(name, []).append((vals[0::2], vals[1::2]))
             i += 41
 
-    def synthesize_fort16(self, seed=0, kick_at_r0=2e-8):
+    def synthesize_fort16(self, seed=0, kick_at_r0=1e-8, decade_per_orders=5.0):
         """Deterministic stand-in for a missing ``fort.16`` (the LHC one is a stripped
         large blob, ``.MISSING_LARGE_BLOBS:1``): Gaussian random multipole errors for every
         occurrence of every type-11 element that has a MULT block, scaled so that each
-        order contributes an r.m.s. kick of ``kick_at_r0`` rad at the reference radius."""
+        order n contributes an r.m.s. kick of ``kick_at_r0 * 10**(-(n-1)/decade_per_orders)``
+        rad at the reference radius (field errors fall off with multipole order)."""
         rng = np.random.default_rng(seed)
         counts = {}
         for nm in self.iter_struct():
@@ -228,9 +229,9 @@ class SixInput:
             m = self.mult[nm]
             nord = len(m["bn"])
             d0 = abs(m["benda"]) if m["benda"] != 0 else 1.0
-            scale = kick_at_r0 / (d0 * 1e-3)
+            scale = kick_at_r0 / (d0 * 1e-3) * 10.0 ** (-np.arange(nord) / decade_per_orders)
             self.multblock[nm] = [
-                (list(rng.normal(0, scale, nord)), list(rng.normal(0, scale, nord)))
+                (list(rng.normal(0, 1, nord) * scale), list(rng.normal(0, 1, nord) * scale))
                 for _ in range(counts[nm])
             ]
 
