@@ -318,3 +318,61 @@ def test_reference_api_semantics_on_device():
     xl.RFMultipole(knl=[0.5, 2, 0.2], ksl=[0.5, 3, 0.1]).track(p1)
     xl.Multipole(knl=[0.5, 2, 0.2], ksl=[0.5, 3, 0.1]).track(q1)
     assert p1.compare(q1, abs_tol=1e-15)
+
+
+# ------------------------------------------------------------------ beam-field elements
+BF_CASES = sorted(k for k, m in H.manifest().items() if m["type"] in BEAMFIELD_TYPES)
+BF_TOL = 1e-12  # relative to the beam r.m.s. of each coordinate (Faddeeva: 4e-14 of |w|)
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("ppt", [1, 2])
+@pytest.mark.parametrize("case", BF_CASES)
+def test_beamfield_elements_match_reference_outputs(case, ppt, strict):
+    m, specs, cols, ref = H.load_case(case)
+    got, line = run_gpu(specs, cols, m["p0c"], m["mass0"], particles_per_thread=ppt, strict=strict)
+    assert "beamfields" in str(line.pack(strict).flags & 2 and "beamfields")
+    assert np.array_equal(got["state"], ref["state"])
+    for k in H.COORDS + ("rpp", "rvv"):
+        err = H.scaled_err(got[k], ref[k])
+        assert err <= BF_TOL, (case, k, err)
+    # the kick itself (what the lens adds), relative to the r.m.s. kick
+    for k in ("px", "py"):
+        kick_ref = ref[k] - cols[k]
+        kick_got = got[k] - cols[k]
+        scale = np.sqrt(np.mean(kick_ref ** 2))
+        if scale > 0:
+            assert np.max(np.abs(kick_got - kick_ref)) <= 2e-10 * scale + 1e-16 * np.max(np.abs(cols[k])), (case, k)
+
+
+def test_bbsimple_lattice_against_oracle():
+    """examples/bbsimple: FODO cell with one 6D and one 4D lens, 3 turns."""
+    from xline_b200 import configs
+
+    line, meta = configs.load_lattice("bbsimple")
+    p0c, m0 = configs.p0c_of(meta)
+    rng = np.random.default_rng(7)
+    n = 600
+    cols = dict(x=rng.normal(0, 2e-3, n), px=rng.normal(0, 2e-4, n), y=rng.normal(0, 2e-3, n),
+                py=rng.normal(0, 2e-4, n), zeta=rng.normal(0, 0.3, n), delta=rng.normal(0, 3e-4, n))
+    p = make_particles(cols, p0c, m0)
+    line.track(p, num_turns=3)
+    got = p.to_numpy()
+    ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=3)
+    for k in H.COORDS:
+        assert H.scaled_err(got[k], ref[k]) <= 5e-12, (k, H.scaled_err(got[k], ref[k]))
+
+
+def test_lhc_beambeam_c3_one_turn_against_oracle():
+    """BASELINE config C3 lattice (72 BeamBeam4D + 2 BeamBeam6D x 15 slices), 300-particle
+    subsample x 1 turn (the oracle needs ~1 s per particle-lens for the 6D lenses)."""
+    from xline_b200 import configs
+
+    line, cols, p0c, m0 = configs.config_lhc_beambeam(300)
+    p = make_particles(cols, p0c, m0)
+    line.track(p, num_turns=1)
+    got = p.to_numpy()
+    ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=1)
+    assert np.array_equal(got["state"], ref["state"])
+    for k in H.COORDS:
+        assert H.scaled_err(got[k], ref[k]) <= FAST_FULL_TURN_TOL, (k, H.scaled_err(got[k], ref[k]))

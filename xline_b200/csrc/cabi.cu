@@ -310,6 +310,20 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   if (segmented) XLB_CUDA(cudaMemsetAsync(s->n_lost, 0, sizeof(unsigned int), st));
 
   if (timed) XLB_CUDA(cudaEventRecord(s->ev0, st));
+  if (o->turns_per_launch > 0) {
+    // particles lost in earlier calls still sit in the caller's arrays (state 0): start from
+    // the compacted survivor list so they do not occupy lanes
+    if ((rc = ensure_compaction_scratch(s, p->n)) != XLB_OK) return rc;
+    if ((rc = compact_alive(a.state, p->n, s->idx, s->block_sums, s->n_active, st)) != XLB_OK)
+      return rc;
+    XLB_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    XLB_CUDA(cudaStreamSynchronize(st));
+    g_stats.compactions += 1;
+    if (static_cast<long long>(s->h_pinned[1]) < p->n) {
+      n_active = static_cast<int>(s->h_pinned[1]);
+      idx = s->idx;
+    }
+  }
   float total_ms = 0.f;
   for (int done = 0; done < o->num_turns && n_active > 0;) {
     const int turns = std::min(seg, o->num_turns - done);

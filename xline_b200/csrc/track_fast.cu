@@ -13,6 +13,18 @@
 
 namespace xlb {
 using namespace XLB_NS;
+#if XLB_BEAMFIELDS
+XLB_DEF_VARIANT(1, 256, 1)
+XLB_DEF_VARIANT(2, 256, 1)
+static const Variant fast_bf_table[] = {
+    XLB_VARIANT_ENTRY("fast/ppt1/t256/beamfields", 1, 256, 1),
+    XLB_VARIANT_ENTRY("fast/ppt2/t256/beamfields", 2, 256, 1),
+};
+const Variant *fast_bf_variants(int *n) {
+  *n = static_cast<int>(sizeof(fast_bf_table) / sizeof(fast_bf_table[0]));
+  return fast_bf_table;
+}
+#else
 XLB_DEF_VARIANT(1, 128, 5)
 XLB_DEF_VARIANT(1, 256, 3)
 XLB_DEF_VARIANT(1, 512, 2)
@@ -43,4 +55,5 @@ const Variant *XLB_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));
   return XLB_TABLE;
 }
+#endif
 }  // namespace xlb

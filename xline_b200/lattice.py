@@ -80,26 +80,16 @@ def _pad(seq, size):
 
 
 def _gauss_field_block(rec, sigma_x, sigma_y, min_sigma_diff):
-    """Five pairs describing a frozen 2-D Gaussian of fixed sigmas
+    """Three pairs describing a frozen 2-D Gaussian of fixed sigmas
     (be_beamfields/gaussian_fields.py:107-121, 5-21, 29-99)."""
+    inv2pieps0 = 1.0 / (2.0 * math.pi * epsilon_0)
     if abs(sigma_x - sigma_y) < min_sigma_diff:
-        sigma = 0.5 * (sigma_x + sigma_y)
-        rec.f(sigma_x, sigma_y).i(0, 0)
-        rec.f(1.0 / (2.0 * math.pi * epsilon_0), -0.5 / (sigma * sigma))
-        rec.f(1.0 / (2.0 * math.pi * epsilon_0 * sigma), 0.0)
-        rec.f(0.0, 0.0)
+        rec.f(sigma_x, sigma_y).i(0, 0).f(inv2pieps0, 0.0)
         return
     if sigma_x == sigma_y:
         # gaussian_fields.py:91-92 -> 1.0/0.0 (tests/test_beamfields.py:86-98)
         raise ZeroDivisionError("float division by zero")
-    kind = 1 if sigma_x > sigma_y else 2
-    big, small = (sigma_x, sigma_y) if kind == 1 else (sigma_y, sigma_x)
-    S = math.sqrt(2.0 * (big * big - small * small))
-    factBE = 1.0 / (2.0 * epsilon_0 * math.sqrt(math.pi) * S)
-    rec.f(sigma_x, sigma_y).i(kind, 0)
-    rec.f(factBE, 1.0 / S)
-    rec.f(small / big, big / small)
-    rec.f(1.0 / (2 * big * big), 1.0 / (2 * small * small))
+    rec.f(sigma_x, sigma_y).i(1 if sigma_x > sigma_y else 2, 0).f(inv2pieps0, 0.0)
 
 
 def _pack_beambeam4d(el, idx):
