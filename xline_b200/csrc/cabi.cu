@@ -449,7 +449,7 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
         case XLB_T_BEAMBEAM6D:
           if (!(lat->flags & XLB_F_BEAMFIELDS))
             return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
-          if (pairs < 8) return fail(XLB_ELATTICE, "bad beam-field record length");
+          if (pairs < 6) return fail(XLB_ELATTICE, "bad beam-field record length");
           break;
         default: {
           char buf[96];

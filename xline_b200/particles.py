@@ -65,10 +65,17 @@ class Particles:
         self.at_turn = mk(cols.get("at_turn", 0), torch.int64)
         pid = cols.get("particle_id")
         self.particle_id = mk(pid if pid is not None else np.arange(n), torch.int64)
-        self._delta = mk(0.0, torch.float64)
-        self.rpp = mk(1.0, torch.float64)
-        self.rvv = mk(1.0, torch.float64)
-        self.delta = mk(cols.get("delta", 0.0), torch.float64)
+        # delta -> (rpp, rvv) in NumPy on the host: the same IEEE operations, in the same
+        # order, as the reference's Pyparticles setter, independent of the device the
+        # columns end up on (torch's CPU and CUDA element-wise kernels differ in the last bit)
+        d = np.array(np.broadcast_to(np.asarray(cols.get("delta", 0.0), dtype=np.float64), (n,)))
+        b0 = self._beta0
+        db0 = d * b0
+        ptaub0 = np.sqrt(db0 ** 2 + 2 * db0 * b0 + 1) - 1
+        opd = 1 + d
+        self._delta = mk(d, torch.float64)
+        self.rvv = mk(opd / (1 + ptaub0), torch.float64)
+        self.rpp = mk(1 / opd, torch.float64)
         if "rpp" in cols:
             self.rpp = mk(cols["rpp"], torch.float64)
         if "rvv" in cols:
