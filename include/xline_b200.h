@@ -89,13 +89,14 @@ enum xlb_tag {
   XLB_T_SPACECHARGE = 17,   /* aux=profile kind (0 coasting,1 q-Gaussian,2 linear
                                interp,3 cubic spline)            spacecharge.py       */
   XLB_T_BEAMBEAM6D = 18,    /* [hdr,(double)n_slices] ...        BB6D.py:15-155       */
-  XLB_T_THIN_BLOCK = 19,    /* fused thin multipole -> [aperture] -> [drift] (pack-time
-                               peephole): aux=order; [hdr,drift_length (0=none)]
-                               [i64 flags,i64 aperture_element_index] (kn_i,ks_i) i=order..0
-                               [hxl,hyl][length,1/length] if flags&1 (curved)
-                               [min_x,max_x][min_y,max_y] if flags&2 (rect; flags&8:
-                               symmetric) or [a*a,b*b][1/(a*a),1/(b*b)] if flags&4      */
-  XLB_T__COUNT = 20
+  XLB_T__COUNT = 19,
+  /* Fused thin multipole -> [aperture] -> [drift] records (pack-time peephole).  The tag
+     has bit 7 set and describes the block: bits 0-1 aperture kind (0 none, 1 symmetric
+     rect, 2 rect, 3 ellipse), bit 2 curved multipole, bit 3 drift present.  aux=order;
+     [hdr,drift_length][i64 aperture_element_index,0] (kn_i,ks_i) i=order..0
+     [hxl,hyl][length,1/length] if curved
+     [min_x,max_x][min_y,max_y] (rect) or [a*a,b*b][1/(a*a),1/(b*b)] (ellipse)            */
+  XLB_T_THIN_BLOCK = 0x80
 };
 
 typedef struct xlb_lattice {

@@ -140,18 +140,21 @@ def test_pack_fuses_multipole_aperture_drift():
                     xl.LimitRect(), xl.Multipole(knl=[0, 0, 1]), xl.LimitRect(min_x=-2, max_x=1)])
     pk = line.pack()
     recs = _walk(pk)
-    T = lattice.T_THIN_BLOCK
-    assert [(r[0], r[2]) for r in recs] == [(T, 0), (T, 3), (lattice.T_LIMIT_RECT, 6), (T, 7)]
+    L = lattice
+    assert [(r[0], r[2]) for r in recs] == [
+        (L.T_THIN_BLOCK | L.AP_ELLIPSE | L.TB_DRIFT, 0), (L.T_THIN_BLOCK | L.TB_CURVED | L.TB_DRIFT, 3),
+        (L.T_LIMIT_RECT, 6), (L.T_THIN_BLOCK | L.AP_RECT, 7)]
     w = pk.words
     f = pk.words.view(np.float64)
-    assert f[1] == 3.0 and int(w[2]) == lattice.TB_ELLIPSE and int(w[3]) == 1
+    assert f[1] == 3.0 and int(w[2]) == 1  # drift length, aperture element index
     size0 = (int(w[0]) >> 16) & 0xFFFF
-    second = 2 * size0
-    assert f[second + 1] == 4.0 and int(w[second + 2]) == lattice.TB_CURVED
-    third = second + 2 * ((int(w[second]) >> 16) & 0xFFFF)
-    assert (int(w[third + 8 - 8]) >> 8) & 0xFF == 1  # symmetric rect flagged in aux
+    assert f[2 * size0 + 1] == 4.0
     line.fuse_records = False
     assert len(_walk(line.pack())) == 8
+    # a symmetric rectangle right after a multipole uses the |x| <= max form (fast encoding only)
+    sym = xl.Line([xl.Multipole(knl=[0, 1]), xl.LimitRect(min_x=-2, max_x=2, min_y=-1, max_y=1)])
+    assert _walk(sym.pack())[0][0] == L.T_THIN_BLOCK | L.AP_RECT_SYM
+    assert _walk(sym.pack(strict=True))[0][0] == L.T_THIN_BLOCK | L.AP_RECT
 
 
 def test_pack_chunking_never_splits_a_record():

@@ -439,11 +439,6 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
         case XLB_T_LIMIT_ELLIPSE: want = 3; break;
         case XLB_T_LIMIT_RECT_ELLIPSE: want = 4; break;
         case XLB_T_MONITOR: want = 5; break;
-        case XLB_T_THIN_BLOCK: {
-          const int fl = static_cast<int>(static_cast<int64_t>(w[pos + 2]));
-          want = 2 + aux + 1 + ((fl & 1) ? 2 : 0) + ((fl & 6) ? 2 : 0);
-          break;
-        }
         case XLB_T_BEAMBEAM4D:
         case XLB_T_SPACECHARGE:
         case XLB_T_BEAMBEAM6D:
@@ -452,6 +447,10 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           if (pairs < 6) return fail(XLB_ELATTICE, "bad beam-field record length");
           break;
         default: {
+          if ((tag & 0xf0) == XLB_T_THIN_BLOCK) {
+            want = 2 + aux + 1 + ((tag & 4) ? 2 : 0) + ((tag & 3) ? 2 : 0);
+            break;
+          }
           char buf[96];
           snprintf(buf, sizeof buf, "unknown tag %d in chunk %d at word %d", tag, c, pos);
           return fail(XLB_ELATTICE, buf);

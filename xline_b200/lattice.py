@@ -334,39 +334,42 @@ class PackedLattice:
         return int(self.words.nbytes)
 
 
-TB_CURVED, TB_RECT, TB_ELLIPSE, TB_RECT_SYM = 1, 2, 4, 8
-T_THIN_BLOCK = 19
+T_THIN_BLOCK = 0x80  # tag family: | aperture kind (bits 0-1) | curved << 2 | drift << 3
+AP_NONE, AP_RECT_SYM, AP_RECT, AP_ELLIPSE = 0, 1, 2, 3
+TB_CURVED, TB_DRIFT = 4, 8
 
 
 def _pack_thin_block(mp, idx, aper, drift, strict):
-    """Fused record XLB_T_THIN_BLOCK: the multipole's kick, then the aperture test, then the
-    drift -- the same maps in the same order as the three separate elements."""
+    """Fused record of the XLB_T_THIN_BLOCK family: the multipole's kick, then the aperture
+    test, then the drift -- the same maps in the same order as the separate elements."""
     order = mp.order
     knl, ksl = _pad(mp.knl, order + 1), _pad(mp.ksl, order + 1)
-    flags = 0
+    tag = T_THIN_BLOCK
     aper_idx = 0
-    if mp.hxl != 0 or mp.hyl != 0:
-        flags |= TB_CURVED
+    curved = mp.hxl != 0 or mp.hyl != 0
+    if curved:
+        tag |= TB_CURVED
     lim = None
     if aper is not None:
         aper_idx, ap = aper
         if type(ap).__name__ == "LimitRect":
-            flags |= TB_RECT
-            if (not strict) and ap.min_x == -ap.max_x and ap.min_y == -ap.max_y:
-                flags |= TB_RECT_SYM
+            sym = (not strict) and ap.min_x == -ap.max_x and ap.min_y == -ap.max_y
+            tag |= AP_RECT_SYM if sym else AP_RECT
             lim = (ap.min_x, ap.max_x, ap.min_y, ap.max_y)
         else:
-            flags |= TB_ELLIPSE
+            tag |= AP_ELLIPSE
             a2, b2 = ap.a * ap.a, ap.b * ap.b
             lim = (a2, b2, 1.0 / a2, 1.0 / b2)
-    rec = _Rec(T_THIN_BLOCK, order, idx, drift[1].length if drift is not None else 0.0)
-    rec.i(flags, aper_idx)
+    if drift is not None:
+        tag |= TB_DRIFT
+    rec = _Rec(tag, order, idx, drift[1].length if drift is not None else 0.0)
+    rec.i(aper_idx, 0)
     for i in range(order, -1, -1):
         if strict:
             rec.f(knl[i], ksl[i])
         else:
             rec.f(knl[i] / _FACT[i], ksl[i] / _FACT[i])
-    if flags & TB_CURVED:
+    if curved:
         rec.f(mp.hxl, mp.hyl).f(mp.length, 1.0 / mp.length if mp.length > 0 else 0.0)
     if lim is not None:
         rec.f(*lim)
