@@ -137,7 +137,7 @@ typedef struct xlb_track_options {
   double *monitor_data;      /* optional BeamMonitor storage (fp64 words), see
                                 XLB_T_MONITOR; same memory space as the particles        */
   int64_t monitor_words;     /* capacity of monitor_data in fp64 words                   */
-  double compact_threshold;  /* re-compact when lost/active exceeds this (default 1/16)  */
+  double compact_threshold;  /* re-compact when lost/active exceeds this (default 1/128) */
 } xlb_track_options_t;
 
 /* Statistics of the last xlb_track_* call on this thread. */

@@ -21,7 +21,7 @@ def main():
     ops = line.algorithmic_ops_per_turn()
     print("elements", len(line), "alg ops/turn", ops)
     for strict in (False,):
-        for ppt, thr in ((1, 128), (1, 256), (1, 512), (2, 128), (2, 256), (3, 128), (4, 128)):
+        for ppt, thr in ((1, 256), (1, 512), (2, 128), (2, 256), (3, 128), (4, 128), (4, 160)):
             p = xl.Particles(p0c=p0c, mass0=m0, **cols)
             try:
                 line.track(p, num_turns=1, particles_per_thread=ppt, threads_per_block=thr, strict=strict)

@@ -302,7 +302,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.n_lost = s->n_lost;
 
   const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch : o->num_turns;
-  const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 16.0);
+  const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 128.0);
   long long n_active = p->n;
   const int *idx = nullptr;
   long long lost_since_compact = 0;

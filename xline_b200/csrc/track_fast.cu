@@ -30,8 +30,9 @@ XLB_DEF_VARIANT(1, 256, 3)
 XLB_DEF_VARIANT(1, 512, 2)
 XLB_DEF_VARIANT(2, 128, 3)
 XLB_DEF_VARIANT(2, 256, 2)
-XLB_DEF_VARIANT(3, 128, 2)
+XLB_DEF_VARIANT(3, 128, 3)
 XLB_DEF_VARIANT(4, 128, 2)
+XLB_DEF_VARIANT(4, 160, 2)
 
 #if XLB_BEAMFIELDS
 #define XLB_TABLE fast_bf_table
@@ -48,8 +49,9 @@ static const Variant XLB_TABLE[] = {
     XLB_VARIANT_ENTRY("fast/ppt1/t512" XLB_SUFFIX, 1, 512, 2),
     XLB_VARIANT_ENTRY("fast/ppt2/t128" XLB_SUFFIX, 2, 128, 3),
     XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_SUFFIX, 2, 256, 2),
-    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 2),
+    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 3),
     XLB_VARIANT_ENTRY("fast/ppt4/t128" XLB_SUFFIX, 4, 128, 2),
+    XLB_VARIANT_ENTRY("fast/ppt4/t160" XLB_SUFFIX, 4, 160, 2),
 };
 const Variant *XLB_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));
