@@ -46,6 +46,41 @@ def main():
             state_mismatch=int((got["state"] != ref["state"]).sum()),
             at_element_mismatch=int((got["at_element"] != ref["at_element"]).sum()),
             err_rel_to_beam_rms=stats(got, ref, alive))
+    # yardstick: the same arithmetic in 80-bit extended precision (x87 long double).  How far
+    # is each float64 implementation from it after one turn?
+    from oracle import xline_oracle as xo
+
+    nl = 400
+    line, cols, p0c, m0 = configs.config_lhc(nl)
+    c64 = {k: v for k, v in cols.items() if k != "particle_id"}
+    pl = xo.OracleParticles(nl, p0c=p0c, mass0=m0, dtype=np.longdouble, **c64)
+    with np.errstate(all="ignore"):
+        xo.line_track(line.to_specs(), pl, 1)
+    truth = xo.gather_full(pl, nl)
+    ref64 = H.run_oracle(line.to_specs(), c64, p0c, m0, num_turns=1)
+    ok = (truth["state"] == 1) & (ref64["state"] == 1)
+    yard = {}
+    for name, arr in (("numpy_float64_oracle", ref64),):
+        yard[name] = stats({k: arr[k].astype(np.float64) for k in COORDS},
+                           {k: truth[k].astype(np.float64) for k in COORDS}, ok)
+    for name, strict in (("gpu_fast", False), ("gpu_strict", True)):
+        p = xl.Particles(p0c=p0c, mass0=m0, **cols)
+        line.track(p, num_turns=1, strict=strict)
+        got = p.to_numpy()
+        # subtract in extended precision, then report relative to the beam r.m.s.
+        yard[name] = {}
+        for k in COORDS:
+            rms = float(np.sqrt(np.mean(truth[k][ok].astype(np.float64) ** 2)))
+            e = np.abs(got[k][ok].astype(np.longdouble) - truth[k][ok]).astype(np.float64) / rms
+            yard[name][k] = dict(median=float(np.median(e)), p99=float(np.quantile(e, 0.99)), max=float(e.max()))
+    e = yard["numpy_float64_oracle"]
+    for k in COORDS:
+        rms = float(np.sqrt(np.mean(truth[k][ok].astype(np.float64) ** 2)))
+        d = np.abs(ref64[k][ok].astype(np.longdouble) - truth[k][ok]).astype(np.float64) / rms
+        e[k] = dict(median=float(np.median(d)), p99=float(np.quantile(d, 0.99)), max=float(d.max()))
+    res["one_turn_distance_to_extended_precision"] = dict(n=nl, **yard)
+    print("vs extended precision, x:", {k: v["x"] for k, v in yard.items()})
+
     n = 20000
     line, cols, p0c, m0 = configs.config_lhc(n)
     amp = np.sqrt(cols["x"] ** 2 + cols["y"] ** 2) / 1e-4
@@ -75,8 +110,10 @@ def main():
     res["notes"] = ("errors are |a-b| / rms(b) per coordinate over particles alive in both runs; "
                     "amplitude = sqrt(x0^2+y0^2)/1e-4 m")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", "accuracy_r1.json"), "w") as fh:
-        json.dump(res, fh, indent=1)
+    for d in ("profiles", "gpurun_out"):  # gpurun_out/ is what travels back from the GPU box
+        os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+        with open(os.path.join(ROOT, d, "accuracy_r1.json"), "w") as fh:
+            json.dump(res, fh, indent=1)
 
 
 if __name__ == "__main__":

@@ -190,7 +190,7 @@ def test_loss_tally_and_compaction_paths_agree():
     b = p2.to_numpy()
     for k in a:
         if k == "s":  # fast kernel: s = s + (sum of drift lengths of the launch); the grouping
-            assert np.allclose(a[k], b[k], rtol=1e-14, atol=0)  # of the sum follows the launches
+            assert np.allclose(a[k], b[k], rtol=1e-11, atol=0)  # of the sum follows the launches
         else:
             assert np.array_equal(a[k], b[k], equal_nan=True), k
     assert np.array_equal(line.loss_tally.cpu().numpy(), tally1.cpu().numpy())
