@@ -138,6 +138,11 @@ typedef struct xlb_track_options {
                                 XLB_T_MONITOR; same memory space as the particles        */
   int64_t monitor_words;     /* capacity of monitor_data in fp64 words                   */
   double compact_threshold;  /* re-compact when lost/active exceeds this (default 1/128) */
+  int32_t turns_per_item;    /* granularity of the device-side work queue: a launch of more
+                                turns than this, over more particle blocks than the device
+                                holds at once, runs persistent CTAs that pull (particle block,
+                                turn segment) items.  0 = default (5), < 0 = off          */
+  int32_t reserved;
 } xlb_track_options_t;
 
 /* Statistics of the last xlb_track_* call on this thread. */

@@ -196,6 +196,33 @@ def test_loss_tally_and_compaction_paths_agree():
     assert np.array_equal(line.loss_tally.cpu().numpy(), tally1.cpu().numpy())
 
 
+def test_work_queue_equals_one_item_per_cta_bitwise():
+    """Persistent CTAs pulling (particle block, turn segment) items must reproduce the plain
+    launch bit for bit (same maps; only the schedule differs), losses included."""
+    from xline_b200 import configs
+
+    n = 200_000  # more particle blocks than the device holds at once -> the queue is used
+    line, cols, p0c, m0 = configs.config_lhc(n)
+    outs = []
+    for tpi in (-1, 5, 2):
+        line.invalidate()
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=11, turns_per_item=tpi)
+        outs.append(p.to_numpy())
+        tally = line.loss_tally.cpu().numpy().copy()
+        if tpi == -1:
+            tally0 = tally
+        else:
+            assert np.array_equal(tally, tally0)
+    assert 0 < (outs[0]["state"] == 0).sum() < n
+    for k in outs[0]:
+        for o in outs[1:]:
+            if k == "s":
+                assert np.allclose(outs[0][k], o[k], rtol=1e-11, atol=0)
+            else:
+                assert np.array_equal(outs[0][k], o[k], equal_nan=True), k
+
+
 def test_compaction_kernel_matches_numpy():
     from xline_b200 import _cabi
 

@@ -138,6 +138,8 @@ struct Scratch {
   int *block_sums = nullptr;  // compaction scratch
   long long cap = 0;          // capacity of idx (entries)
   int nblocks_cap = 0;
+  unsigned int *queue = nullptr;   // work queue of the persistent kernel: head + per-block progress
+  size_t queue_cap = 0;
   unsigned int *n_lost = nullptr;  // device counter
   int *n_active = nullptr;         // device survivor count
   unsigned int *h_pinned = nullptr;  // [0]=n_lost, [1]=n_active (pinned host)
@@ -169,6 +171,17 @@ static int get_scratch(Scratch **out) {
   XLB_CUDA(cudaEventCreate(&s->ev1));
   g_scratch.push_back(s);
   *out = s;
+  return XLB_OK;
+}
+
+static int ensure_queue(Scratch *s, size_t words) {
+  if (words > s->queue_cap) {
+    if (s->queue) cudaFree(s->queue);
+    s->queue = nullptr;
+    s->queue_cap = 0;
+    XLB_CUDA(cudaMalloc(&s->queue, words * sizeof(unsigned int)));
+    s->queue_cap = words;
+  }
   return XLB_OK;
 }
 
@@ -278,7 +291,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   if ((rc = get_scratch(&s)) != XLB_OK) return rc;
 
   const size_t chunk_bytes = static_cast<size_t>(lat->chunk_words) * 8;
-  const size_t smem = XLB_STAGES * chunk_bytes + 2 * XLB_STAGES * sizeof(unsigned long long);
+  const size_t smem = XLB_STAGES * chunk_bytes + (2 * XLB_STAGES + 2) * sizeof(unsigned long long);
   XLB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   cudaFuncAttributes fa;
@@ -301,6 +314,13 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.mon_words = o->monitor_words;
   a.n_lost = s->n_lost;
 
+  int occ = 1;
+  XLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, threads, smem));
+  int dev = 0, sms = 0;
+  XLB_CUDA(cudaGetDevice(&dev));
+  XLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int resident = std::max(1, occ) * sms;  // CTAs the device holds at once
+  const int tpi = (o->turns_per_item == 0) ? 5 : o->turns_per_item;
   const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch : o->num_turns;
   const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 128.0);
   long long n_active = p->n;
@@ -332,7 +352,24 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     a.idx = idx;
     const long long per_block = static_cast<long long>(threads) * v->ppt;
     const int blocks = static_cast<int>((n_active + per_block - 1) / per_block);
-    v->launch(a, blocks, threads, smem, st);
+    int grid = blocks;
+    a.queue = nullptr;
+    a.n_blocks = static_cast<unsigned int>(blocks);
+    a.n_items = static_cast<unsigned int>(blocks);
+    a.turns_per_item = turns;
+    if (tpi > 0 && turns > tpi && blocks > resident) {
+      // persistent CTAs + device-side work queue: (block, turn segment) items, segment-major
+      const long long segs = (turns + tpi - 1) / tpi;
+      if (static_cast<long long>(blocks) * segs < 0xffffffffLL) {
+        if ((rc = ensure_queue(s, static_cast<size_t>(blocks) + 1)) != XLB_OK) return rc;
+        XLB_CUDA(cudaMemsetAsync(s->queue, 0, (static_cast<size_t>(blocks) + 1) * sizeof(unsigned int), st));
+        a.queue = s->queue;
+        a.n_items = static_cast<unsigned int>(blocks * segs);
+        a.turns_per_item = tpi;
+        grid = resident;
+      }
+    }
+    v->launch(a, grid, threads, smem, st);
     XLB_CUDA(cudaGetLastError());
     g_stats.kernel_launches += 1;
     g_stats.blocks = blocks;

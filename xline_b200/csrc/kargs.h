@@ -24,6 +24,11 @@ struct KArgs {
   double *mon;
   long long mon_words;
   unsigned int *n_lost;  // device counter, incremented per lost particle
+  // work queue (nullptr = one item per CTA): [0] = next item, [1 + b] = segments published
+  // for particle block b.  n_items = n_blocks * ceil(num_turns / turns_per_item).
+  unsigned int *queue;
+  unsigned int n_blocks, n_items;
+  int turns_per_item;
 };
 
 struct Variant {

@@ -192,7 +192,7 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ the hot path
     def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
-              threads_per_block=0, timed=False):
+              threads_per_block=0, timed=False, turns_per_item=0):
         """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
         times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
         returns ``None`` like the reference.
@@ -231,6 +231,7 @@ class Line(E.Element):
             opts.particles_per_thread = int(particles_per_thread)
             opts.threads_per_block = int(threads_per_block)
             opts.turns_per_launch = int(turns_per_launch)
+            opts.turns_per_item = int(turns_per_item)
             opts.loss_tally = self.loss_tally.data_ptr()
             if packed.monitor_words > 0:
                 if self._monitor_buf is None or self._monitor_buf.device != p.device:
