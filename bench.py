@@ -43,8 +43,8 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
     ap.add_argument("--turns-per-step", type=int, default=100)
     ap.add_argument("--turns-per-launch", type=int, default=50)
-    ap.add_argument("--ppt", type=int, default=2)
-    ap.add_argument("--threads", type=int, default=256)
+    ap.add_argument("--ppt", type=int, default=3)
+    ap.add_argument("--threads", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-particles", type=int, default=5000, help="CPU sample: particles per process")
     ap.add_argument("--no-cpu-baseline", action="store_true")

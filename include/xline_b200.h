@@ -126,8 +126,10 @@ typedef struct xlb_particles {
 
 typedef struct xlb_track_options {
   int32_t num_turns;         /* >= 0                                                     */
-  int32_t particles_per_thread; /* 0 = default (2); 1, 2 or 4                            */
-  int32_t threads_per_block;    /* 0 = default (256); multiple of 32, <= 512             */
+  int32_t particles_per_thread; /* 0 = default (3; 2 for strict / beam-field lattices);
+                                   1..4                                                    */
+  int32_t threads_per_block;    /* 0 = default (128 at 3 particles/thread, else 256);
+                                   multiple of 32, <= the variant's launch bound           */
   int32_t turns_per_launch;  /* 0 = all turns in one launch; otherwise survivors are
                                 re-compacted (warp-ballot stream compaction) between
                                 launches of this many turns                              */

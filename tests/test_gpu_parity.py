@@ -52,7 +52,7 @@ def run_gpu(specs, cols, p0c, mass0, num_turns=1, **kw):
     return p.to_numpy(), line
 
 
-@pytest.mark.parametrize("ppt", [1, 2, 4])
+@pytest.mark.parametrize("ppt", [1, 2, 3, 4])
 @pytest.mark.parametrize("case", LEAN_CASES)
 def test_fast_kernel_matches_reference_outputs(case, ppt):
     m, specs, cols, ref = H.load_case(case)

@@ -279,11 +279,14 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
 
   const bool strict = (lat->flags & XLB_F_STRICT) != 0;
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
-  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread : 2;
-  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : 256;
+  // defaults from the B200 sweep (scripts/probe_bench_sweep.py): thin-lens lattices run best
+  // with 3 particles per thread in 128-thread CTAs (3 CTAs/SM, 164 registers, no spills)
+  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread
+                                                  : ((strict || beamfields) ? 2 : 3);
+  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (ppt_req == 3 ? 128 : 256);
   const Variant *v = pick_variant(strict, beamfields, ppt_req, threads_req);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
-  int threads = o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, 256);
+  int threads = o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req);
   if (threads % 32 || threads > v->threads)
     return fail(XLB_EINVAL, "threads_per_block must be a multiple of 32 and <= the variant's limit");
 
