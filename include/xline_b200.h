@@ -92,7 +92,8 @@ enum xlb_tag {
   XLB_T__COUNT = 19,
   /* Fused thin multipole -> [aperture] -> [drift] records (pack-time peephole).  The tag
      has bit 7 set and describes the block: bits 0-1 aperture kind (0 none, 1 symmetric
-     rect, 2 rect, 3 ellipse), bit 2 curved multipole, bit 3 drift present.  aux=order;
+     rect, 2 rect, 3 ellipse), bit 2 curved multipole, bit 3 drift present, bit 4 that drift
+     is a DriftExact.  aux=order;
      [hdr,drift_length][i64 aperture_element_index,0] (kn_i,ks_i) i=order..0
      [hxl,hyl][length,1/length] if curved
      [min_x,max_x][min_y,max_y] (rect) or [a*a,b*b][1/(a*a),1/(b*b)] (ellipse)            */

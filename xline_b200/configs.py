@@ -87,3 +87,121 @@ def config_lhc_beambeam(n=10_000_000, rank=0, first_id=0):
     p0c, m0 = p0c_of(meta)
     return line, gaussian_beam(n, 3, rank, sx=2e-4, spx=2e-6, sz=0.075, amp_max=6.0,
                                first_id=first_id), p0c, m0
+
+
+# ---------------------------------------------------------------------------------------
+# Synthetic stand-ins for the MAD-X based configurations (C4 PETRA IV, C5 PSB): the
+# reference builds those lattices with cpymad + MAD-X `makethin`, neither of which exists
+# here.  The generators below reproduce the element *mix* and sizes the
+# survey extracted from examples/petra4/h7ba_n8.seq and tests/psb/*, on simple stable
+# optics, so that parity and throughput of those element types can be measured.
+# ---------------------------------------------------------------------------------------
+ELECTRON_MASS_EV = 0.51099895e6
+
+
+def config_psb_like(n=1_000_000, rank=0, n_cells=16, sc_per_cell=8, monitor_stores=0, monitor_ids=0):
+    """C5 stand-in: a 157 m proton ring at p0c = 0.571 GeV (tests/psb/psb_fb_lhc.madx:14) made
+    of 16 FODO cells with curved thin dipoles, DipoleEdge pairs, 128 SCQGaussProfile kicks per
+    turn (reference: 120, tests/test_madx_import.py:19; 1e11 protons, bunchlength_rms = 1 m,
+    :30-33), the PSB aperture mix (circle / ellipse / rect-ellipse / rectangle) and a h = 1
+    cavity; optionally one BeamMonitor."""
+    from .particles import PROTON_MASS_EV
+
+    p0c, m0 = 0.571e9, PROTON_MASS_EV
+    circ = 157.08
+    lc = circ / n_cells
+    kq = 0.24  # thin-quad strength [1/m]: ~72 degrees per cell
+    bend = 2 * np.pi / (2 * n_cells)
+    seg = lc / 2 / (sc_per_cell // 2)  # drift between space-charge kicks
+    els, names = [], []
+
+    def add(el, nm):
+        els.append(el)
+        names.append(nm)
+
+    beta_max, beta_min = 16.0, 5.0
+    eps = 2.5e-6 / (0.608 * 1.17)  # normalised 2.5 um at beta*gamma = 0.712
+    for c in range(n_cells):
+        for half, (k1l, bx, by) in enumerate(((kq, beta_max, beta_min), (-kq, beta_min, beta_max))):
+            tag = "c%d.%s" % (c, "f" if half == 0 else "d")
+            add(E.Multipole(knl=[0.0, k1l], ksl=[0.0, 0.0]), "q" + tag)
+            ap_kind = (c + half) % 4
+            if ap_kind == 0:
+                add(E.LimitEllipse(a=0.05, b=0.05), "ap" + tag)          # circle
+            elif ap_kind == 1:
+                add(E.LimitEllipse(a=0.06, b=0.035), "ap" + tag)
+            elif ap_kind == 2:
+                add(E.LimitRectEllipse(max_x=0.05, max_y=0.03, a=0.06, b=0.04), "ap" + tag)
+            else:
+                add(E.LimitRect(min_x=-0.055, max_x=0.055, min_y=-0.032, max_y=0.032), "ap" + tag)
+            for k in range(sc_per_cell // 2):
+                add(E.Drift(length=seg / 2), "d%s.%da" % (tag, k))
+                f = (k + 0.5) / (sc_per_cell // 2)
+                sx = float(np.sqrt(eps * (bx + (by - bx) * f)))
+                sy = float(np.sqrt(eps * (by + (bx - by) * f)))
+                add(E.SCQGaussProfile(number_of_particles=1e11, bunchlength_rms=1.0, sigma_x=sx,
+                                      sigma_y=sy, length=seg, x_co=0.0, y_co=0.0), "sc%s.%d" % (tag, k))
+                if k == 0:
+                    add(E.DipoleEdge(h=bend / 1.6, e1=bend / 2, hgap=0.03, fint=0.5), "e1" + tag)
+                    add(E.Multipole(knl=[bend], ksl=[0.0], hxl=bend, hyl=0.0, length=1.6), "b" + tag)
+                    add(E.DipoleEdge(h=bend / 1.6, e1=bend / 2, hgap=0.03, fint=0.5), "e2" + tag)
+                add(E.Drift(length=seg / 2), "d%s.%db" % (tag, k))
+        if c == 0 and monitor_stores > 0:
+            add(E.BeamMonitor(num_stores=monitor_stores, start=0, skip=1, min_particle_id=0,
+                              max_particle_id=max(monitor_ids - 1, 0)), "monitor")
+    e0 = np.sqrt(p0c ** 2 + m0 ** 2)
+    frev = (p0c / e0) * 299792458.0 / circ
+    add(E.Cavity(voltage=8e3, frequency=frev, lag=0.0), "cav")
+    rng = np.random.default_rng(SEED0 + 1000 * 5 + rank)
+    cols = dict(
+        x=rng.normal(0, 4e-3, n), px=rng.normal(0, 4e-4, n), y=rng.normal(0, 3e-3, n),
+        py=rng.normal(0, 3e-4, n), zeta=rng.normal(0, 1.0, n), delta=rng.normal(0, 1e-3, n),
+    )
+    return Line(els, names), cols, p0c, m0
+
+
+def config_petra_like(n=1_000_000, rank=0, n_cells=120, grid=None):
+    """C4 stand-in: a 6 GeV electron ring (examples/petra4/track_p1.py:21) of 120 cells whose
+    quadrupoles and bends are 4-slice thin lenses (track_p1.py:26-30) separated by exact
+    drifts, with sextupoles, two 500 MHz cavities and two RFMultipoles (h7ba_n8.seq:259,918,
+    923 for the RF) -- about 5.6k elements per turn.  The beam is a dynamic-aperture scan: a
+    2-D grid of (x, y) amplitudes, interleaved across ranks when sharded."""
+    p0c, m0 = 6e9, ELECTRON_MASS_EV
+    lc = 2304.0 / n_cells
+    kq = 4 * np.sin(np.radians(40.0)) / lc  # 80 degrees per cell
+    bend = 2 * np.pi / (2 * n_cells)
+    els, names = [], []
+
+    def add(el, nm):
+        els.append(el)
+        names.append(nm)
+
+    dq = 0.05  # drift between slices
+    dl = (lc / 2 - 4 * dq * 2) / 2
+    for c in range(n_cells):
+        for half, sgn in enumerate((1.0, -1.0)):
+            tag = "%d.%d" % (c, half)
+            for sl in range(4):
+                add(E.Multipole(knl=[0.0, sgn * kq / 4], ksl=[0.0, 0.0]), "q%s.%d" % (tag, sl))
+                add(E.DriftExact(length=dq), "dq%s.%d" % (tag, sl))
+            add(E.Multipole(knl=[0.0, 0.0, sgn * 1.5], ksl=[0.0, 0.0, 0.0]), "s" + tag)
+            add(E.DriftExact(length=dl), "d1" + tag)
+            for sl in range(4):
+                add(E.Multipole(knl=[bend / 4], ksl=[0.0], hxl=bend / 4, hyl=0.0, length=0.4),
+                    "b%s.%d" % (tag, sl))
+                add(E.DriftExact(length=dq), "db%s.%d" % (tag, sl))
+            add(E.DriftExact(length=dl), "d2" + tag)
+        if c in (0, n_cells // 2):
+            add(E.Cavity(voltage=4e6, frequency=499.6e6, lag=180.0), "cav%d" % c)
+            add(E.RFMultipole(voltage=0.0, frequency=499.6e6, lag=0.0, knl=[0.0, 1e-4], ksl=[0.0, 0.0],
+                              pn=[0.0, 90.0], ps=[0.0, 0.0]), "rfm%d" % c)
+            add(E.LimitEllipse(a=0.01, b=0.005), "ap%d" % c)
+    if grid is None:
+        side = int(np.ceil(np.sqrt(n)))
+        gx, gy = np.meshgrid(np.linspace(0, 4e-3, side), np.linspace(0, 2e-3, side))
+        x0, y0 = gx.ravel()[:n], gy.ravel()[:n]
+    else:
+        x0, y0 = grid
+    cols = dict(x=x0.copy(), px=np.zeros(n), y=y0.copy(), py=np.zeros(n), zeta=np.zeros(n),
+                delta=np.zeros(n))
+    return Line(els, names), cols, p0c, m0

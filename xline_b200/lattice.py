@@ -334,9 +334,9 @@ class PackedLattice:
         return int(self.words.nbytes)
 
 
-T_THIN_BLOCK = 0x80  # tag family: | aperture kind (bits 0-1) | curved << 2 | drift << 3
+T_THIN_BLOCK = 0x80  # tag family: | aperture kind (bits 0-1) | curved << 2 | drift << 3 | exact << 4
 AP_NONE, AP_RECT_SYM, AP_RECT, AP_ELLIPSE = 0, 1, 2, 3
-TB_CURVED, TB_DRIFT = 4, 8
+TB_CURVED, TB_DRIFT, TB_DRIFT_EXACT = 4, 8, 16
 
 
 def _pack_thin_block(mp, idx, aper, drift, strict):
@@ -362,6 +362,8 @@ def _pack_thin_block(mp, idx, aper, drift, strict):
             lim = (a2, b2, 1.0 / a2, 1.0 / b2)
     if drift is not None:
         tag |= TB_DRIFT
+        if type(drift[1]).__name__ == "DriftExact":
+            tag |= TB_DRIFT_EXACT
     rec = _Rec(tag, order, idx, drift[1].length if drift is not None else 0.0)
     rec.i(aper_idx, 0)
     for i in range(order, -1, -1):
@@ -399,7 +401,7 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             if pos < len(live) and type(live[pos][1]).__name__ in ("LimitRect", "LimitEllipse"):
                 aper = live[pos]
                 pos += 1
-            if pos < len(live) and type(live[pos][1]).__name__ == "Drift":
+            if pos < len(live) and type(live[pos][1]).__name__ in ("Drift", "DriftExact"):
                 drift = live[pos]
                 pos += 1
             rec = _pack_thin_block(el, idx, aper, drift, strict)
