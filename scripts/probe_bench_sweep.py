@@ -10,8 +10,11 @@ from xline_b200 import configs
 n, turns = 1_000_000, 40
 line, cols, p0c, m0 = configs.config_lhc(n)
 ALL = ((2, 256, 5), (2, 256, 2), (2, 256, 10), (2, 256, -1), (3, 128, 5), (4, 128, 5), (2, 128, 5), (1, 512, 5),
-       (3, 128, -1), (1, 512, -1), (1, 256, 5), (1, 128, 5))
-sel = [ALL[int(a)] for a in sys.argv[1:]] or ALL
+       (3, 128, -1), (1, 512, -1), (1, 256, 5), (1, 128, 5), (3, 128, 3), (3, 128, 10), (3, 96, 5), (4, 128, 5), (3, 64, 5))
+sel = [ALL[int(a)] for a in sys.argv[1:] if not a.startswith("cw=")] or ALL
+for a in sys.argv[1:]:
+    if a.startswith("cw="):
+        line.chunk_words = int(a[3:])
 for ppt, thr, tpi in sel:
     p = xl.Particles(p0c=p0c, mass0=m0, **cols)
     line.track(p, num_turns=2, particles_per_thread=ppt, threads_per_block=thr, turns_per_item=tpi)

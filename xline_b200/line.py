@@ -29,6 +29,7 @@ class Line(E.Element):
         assert len(self.elements) == len(self.element_names)  # xline/line.py:38
         self._cache = {}
         self.fuse_records = True  # pack-time peephole: multipole -> aperture -> drift in one record
+        self.chunk_words = None   # 8-byte words per TMA chunk (None = lattice.DEFAULT_CHUNK_WORDS)
         self._monitor_buf = None
         self.loss_tally = None
         self.last_stats = None
@@ -168,6 +169,8 @@ class Line(E.Element):
 
     def pack(self, strict=False, chunk_words=None):
         """Host-side packed lattice (``lattice.PackedLattice``), cached."""
+        if chunk_words is None:
+            chunk_words = self.chunk_words
         key = ("host", bool(strict), chunk_words, self.fuse_records, tuple(map(id, self.elements)))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
