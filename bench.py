@@ -217,7 +217,6 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.particles
@@ -373,9 +372,19 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    # Exactly one JSON line on stdout: libraries (NCCL's version banner, ...) write to fd 1
+    # behind Python's back, so fd 1 is pointed at stderr for the run and the line goes to a
+    # duplicate of the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_b200(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
