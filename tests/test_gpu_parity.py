@@ -458,3 +458,67 @@ def test_petra_like_c4_against_oracle():
     assert np.array_equal(got2["state"], ref["state"])
     for k in H.COORDS:  # reference operation order: sin/cos/sqrt ulp differences only
         assert H.scaled_err(got2[k][alive], ref[k][alive]) <= 1e-12, (k, H.scaled_err(got2[k][alive], ref[k][alive]))
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_empty_single_all_lost_nan():
+    import xline_b200 as xl
+
+    line = xl.Line([xl.Drift(length=1.0), xl.Multipole(knl=[0, 0.1]),
+                    xl.LimitRect(min_x=-1e-2, max_x=1e-2, min_y=-1e-2, max_y=1e-2), xl.Drift(length=2.0)])
+    # empty particle set and zero turns: no launch, no error
+    p0 = xl.Particles(p0c=1e9, x=np.zeros(0))
+    line.track(p0, num_turns=3)
+    assert len(p0) == 0
+    p1 = xl.Particles(p0c=1e9, x=[1e-3, 2e-3])
+    line.track(p1, num_turns=0)
+    assert p1.at_turn.tolist() == [0, 0] and p1.x.tolist() == [1e-3, 2e-3]
+    # one particle given as scalars (reference tests/test_track.py:57-61): state flips to 0
+    ps = xl.Particles(p0c=1e9, x=1.0, y=1.0)
+    line.track(ps)
+    assert ps.state.tolist() == [0] and ps.at_element.tolist() == [2] and ps.at_turn.tolist() == [0]
+    # NaN compares false in every bound -> lost at the first aperture, coordinates kept
+    pn = xl.Particles(p0c=1e9, x=[np.nan, 1e-3, 0.5], y=[0.0, 0.0, 0.0])
+    line.track(pn, num_turns=2)
+    assert pn.state.tolist() == [0, 1, 0] and pn.at_turn.tolist() == [0, 2, 0]
+    assert np.isnan(pn.x[0].item()) and pn.at_element.tolist() == [2, 0, 2]
+    # everything lost in the first turn; tracking on is a no-op on the frozen particles
+    pa = xl.Particles(p0c=1e9, x=np.full(700, 0.5))
+    line.loss_tally.zero_()  # the tally accumulates over calls on the same Line
+    line.track(pa, num_turns=2, turns_per_launch=1)
+    snap = pa.to_numpy()
+    line.track(pa, num_turns=5, turns_per_launch=2)
+    again = pa.to_numpy()
+    assert (snap["state"] == 0).all() and int(line.loss_tally[2]) == 700
+    for k in snap:
+        assert np.array_equal(snap[k], again[k], equal_nan=True), k
+    # empty line: only the turn counter advances
+    pe = xl.Particles(p0c=1e9, x=[1e-3])
+    xl.Line([]).track(pe, num_turns=4)
+    assert pe.at_turn.tolist() == [4] and pe.x.tolist() == [1e-3]
+    # non-contiguous columns are made contiguous, values preserved
+    pc = xl.Particles(p0c=1e9, x=np.linspace(0, 1e-3, 10))
+    pc.x = torch.linspace(0, 1e-3, 20, dtype=torch.float64, device="cuda")[::2]
+    before = pc.x.clone()
+    xl.Line([xl.XYShift(dx=1e-4)]).track(pc)
+    assert torch.equal(pc.x, before - 1e-4)
+
+
+def test_monitor_rolling_and_skip():
+    import xline_b200 as xl
+
+    n, turns = 64, 11
+    mon = xl.BeamMonitor(num_stores=2, start=1, skip=3, min_particle_id=0, max_particle_id=n - 1,
+                         is_rolling=True)
+    line = xl.Line([xl.Drift(length=1.0), mon])
+    rng = np.random.default_rng(2)
+    cols = dict(x=rng.normal(0, 1e-3, n), px=rng.normal(0, 1e-4, n))
+    p = make_particles(cols, 1e9, 938.27208816e6)
+    line.track(p, num_turns=turns)
+    monitors = {}
+    H.run_oracle(line.to_specs(), cols, 1e9, 938.27208816e6, num_turns=turns, monitors=monitors)
+    store = monitors[1]
+    # stores happen at turns 1, 4, 7, 10 -> slots 0, 1, 0, 1: the last two survive
+    assert sorted(set(store["at_turn"].ravel().tolist())) == [7, 10]
+    assert np.array_equal(mon.data["at_turn"].cpu().numpy(), store["at_turn"].astype(float))
+    assert np.array_equal(mon.data["x"].cpu().numpy(), store["x"])
