@@ -97,7 +97,16 @@ enum xlb_tag {
      [hdr,drift_length][i64 aperture_element_index,0] (kn_i,ks_i) i=order..0
      [hxl,hyl][length,1/length] if curved
      [min_x,max_x][min_y,max_y] (rect) or [a*a,b*b][1/(a*a),1/(b*b)] (ellipse)            */
-  XLB_T_THIN_BLOCK = 0x80
+  XLB_T_THIN_BLOCK = 0x80,
+  /* Merged block (fast encoding only): two co-located thin multipoles K1, K2 evaluated as ONE
+     multipole with summed coefficients -- [K1][A1][K2][A2][drift] of the Line, where thin kicks
+     leave x, y untouched so both aperture tests are unaffected.  Tag = 0xA0 | the thin-block
+     bits (A2 kind, K2 curved, drift, exact).  aux = merged order;
+     [hdr,drift_length][i64 a1_index | a2_index << 32, i64 k1_order | has_a1 << 8]
+     merged (kn_i,ks_i) i=order..0  [hxl,hyl][length,1/length][knl0,ksl0 of K2] if curved
+     [a*a,b*b][1/(a*a),1/(b*b)] if has_a1 (A1 is an ellipse)  A2 limits as above
+     K1's own (kn_i,ks_i) i=k1_order..0 (re-evaluated only for particles lost at A1)        */
+  XLB_T_MERGED_BLOCK = 0xA0
 };
 
 typedef struct xlb_lattice {

@@ -155,6 +155,7 @@ def test_fused_records_equal_unfused_bitwise():
     from xline_b200 import configs
 
     line, cols, p0c, m0 = configs.config_lhc(20_000)
+    line.merge_multipoles = False  # merging sums coefficients: exact in real arithmetic only
     outs = []
     for fuse in (True, False):
         line.fuse_records = fuse
@@ -167,6 +168,38 @@ def test_fused_records_equal_unfused_bitwise():
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[2][k], equal_nan=True), ("fast", k)
         assert np.array_equal(outs[1][k], outs[3][k], equal_nan=True), ("strict", k)
+
+
+def test_merged_multipoles_match_separate_kicks():
+    """Pack-time merging of co-located thin multipoles ([K1][A1][K2][A2][drift] -> one summed
+    kick): same losses at the same places and turns, coordinates equal to rounding noise, and
+    particles lost at A1 frozen with the momentum they had after K1 only."""
+    from xline_b200 import configs
+
+    n = 40_000
+    line, cols, p0c, m0 = configs.config_lhc(n)
+    cols["x"][:4000] *= 6.0  # plenty of losses, at A1 apertures too
+    res = []
+    for merge in (True, False):
+        line.merge_multipoles = merge
+        line.invalidate()
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=1)
+        res.append((p.to_numpy(), line.loss_tally.cpu().numpy().copy(), line.pack().record_counts))
+    (a, ta, ca), (b, tb, cb) = res
+    assert sum(ca.values()) < sum(cb.values()) and any(k & 0x20 and k & 0x80 for k in ca)
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["at_element"], b["at_element"])
+    assert np.array_equal(a["at_turn"], b["at_turn"]) and np.array_equal(ta, tb)
+    lost = a["state"] == 0
+    assert lost.sum() > 1000
+    a1_elements = {i for i, el in enumerate(line.elements) if type(el).__name__ == "LimitEllipse"}
+    assert sum(int(e) in a1_elements for e in a["at_element"][lost]) > 10
+    for k in H.COORDS:
+        assert H.scaled_err(a[k][~lost], b[k][~lost]) <= FAST_FULL_TURN_TOL, k
+        assert H.scaled_err(a[k][lost], b[k][lost]) <= FAST_FULL_TURN_TOL, ("lost", k)
+    # first-turn losses: momentum frozen after K1 only -> equal to rounding of the single kick
+    first = lost & (a["at_turn"] == 0)
+    assert np.allclose(a["px"][first], b["px"][first], rtol=1e-11, atol=1e-16)
 
 
 def test_loss_tally_and_compaction_paths_agree():

@@ -491,6 +491,13 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
             want = 2 + aux + 1 + ((tag & 4) ? 2 : 0) + ((tag & 3) ? 2 : 0);
             break;
           }
+          if ((tag & 0xe0) == XLB_T_MERGED_BLOCK) {
+            if (lat->flags & XLB_F_STRICT) return fail(XLB_ELATTICE, "merged block in a strict lattice");
+            const int64_t f = static_cast<int64_t>(w[pos + 3]);
+            want = 2 + aux + 1 + ((tag & 4) ? 3 : 0) + (((f >> 8) & 1) ? 2 : 0) + ((tag & 3) ? 2 : 0) +
+                   static_cast<int>(f & 0xff) + 1;
+            break;
+          }
           char buf[96];
           snprintf(buf, sizeof buf, "unknown tag %d in chunk %d at word %d", tag, c, pos);
           return fail(XLB_ELATTICE, buf);

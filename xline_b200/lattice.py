@@ -378,7 +378,86 @@ def _pack_thin_block(mp, idx, aper, drift, strict):
     return rec
 
 
-def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True, fuse=True):
+T_MERGED_BLOCK = 0xA0  # thin-block bits | 0x20: two co-located multipoles as one (fast only)
+MERGE_MAX_K1_ORDER = 4
+
+
+def _pack_merged_block(k1, idx1, a1, k2, idx2, a2, drift):
+    """XLB_T_MERGED_BLOCK: [K1][A1 ellipse?][K2][A2?][drift?] with the two thin kicks summed
+    into one coefficient set (fast encoding only; see include/xline_b200.h)."""
+    order = max(k1.order, k2.order)
+    kn = _pad(k1.knl, order + 1) + _pad(k2.knl, order + 1)
+    ks = _pad(k1.ksl, order + 1) + _pad(k2.ksl, order + 1)
+    tag = T_MERGED_BLOCK
+    curved = k2.hxl != 0 or k2.hyl != 0
+    if curved:
+        tag |= TB_CURVED
+    lim2 = None
+    a2_idx = 0
+    if a2 is not None:
+        a2_idx, ap = a2
+        if type(ap).__name__ == "LimitRect":
+            sym = ap.min_x == -ap.max_x and ap.min_y == -ap.max_y
+            tag |= AP_RECT_SYM if sym else AP_RECT
+            lim2 = (ap.min_x, ap.max_x, ap.min_y, ap.max_y)
+        else:
+            tag |= AP_ELLIPSE
+            aa, bb = ap.a * ap.a, ap.b * ap.b
+            lim2 = (aa, bb, 1.0 / aa, 1.0 / bb)
+    if drift is not None:
+        tag |= TB_DRIFT
+        if type(drift[1]).__name__ == "DriftExact":
+            tag |= TB_DRIFT_EXACT
+    rec = _Rec(tag, order, idx2, drift[1].length if drift is not None else 0.0)
+    a1_idx = a1[0] if a1 is not None else 0
+    rec.i(a1_idx | (a2_idx << 32), k1.order | ((1 if a1 is not None else 0) << 8))
+    for i in range(order, -1, -1):
+        rec.f(kn[i] / _FACT[i], ks[i] / _FACT[i])
+    if curved:
+        rec.f(k2.hxl, k2.hyl).f(k2.length, 1.0 / k2.length if k2.length > 0 else 0.0)
+        rec.f(_pad(k2.knl, 1)[0], _pad(k2.ksl, 1)[0])
+    if a1 is not None:
+        aa, bb = a1[1].a * a1[1].a, a1[1].b * a1[1].b
+        rec.f(aa, bb, 1.0 / aa, 1.0 / bb)
+    if lim2 is not None:
+        rec.f(*lim2)
+    k1n, k1s = _pad(k1.knl, k1.order + 1), _pad(k1.ksl, k1.order + 1)
+    for i in range(k1.order, -1, -1):
+        rec.f(k1n[i] / _FACT[i], k1s[i] / _FACT[i])
+    return rec
+
+
+def _try_merge(live, pos):
+    """Match [K1 straight, low order][LimitEllipse?][K2][LimitRect|LimitEllipse?][Drift?]
+    starting at live[pos]; returns (record, new_pos) or None."""
+    def kind(i):
+        return type(live[i][1]).__name__ if i < len(live) else None
+
+    idx1, k1 = live[pos]
+    if k1.hxl != 0 or k1.hyl != 0 or k1.order > MERGE_MAX_K1_ORDER:
+        return None
+    i = pos + 1
+    a1 = None
+    if kind(i) == "LimitEllipse":
+        a1 = live[i]
+        i += 1
+    if kind(i) != "Multipole":
+        return None
+    idx2, k2 = live[i]
+    i += 1
+    a2 = None
+    if kind(i) in ("LimitRect", "LimitEllipse"):
+        a2 = live[i]
+        i += 1
+    drift = None
+    if kind(i) in ("Drift", "DriftExact"):
+        drift = live[i]
+        i += 1
+    return _pack_merged_block(k1, idx1, a1, k2, idx2, a2, drift), i
+
+
+def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True, fuse=True,
+              merge=True):
     """Pack ``elements`` (the ``Line.elements`` list).  ``element_index`` in every record
     is the position in that list, so ``at_element`` matches the reference's indexing even
     though exact no-ops (zero-length drifts, all-zero multipoles, disabled lenses) are not
@@ -395,7 +474,11 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
         idx, el = live[pos]
         pos += 1
         name = type(el).__name__
-        if fuse and name == "Multipole":
+        merged = _try_merge(live, pos - 1) if (fuse and merge and not strict and name == "Multipole") else None
+        if merged is not None:
+            # two co-located thin multipoles (apertures in between allowed): one summed kick
+            rec, pos = merged
+        elif fuse and name == "Multipole":
             # peephole: thin multipole -> [LimitRect | LimitEllipse] -> [Drift] in one record
             aper = drift = None
             if pos < len(live) and type(live[pos][1]).__name__ in ("LimitRect", "LimitEllipse"):

@@ -30,6 +30,7 @@ class Line(E.Element):
         self._cache = {}
         self.fuse_records = True  # pack-time peephole: multipole -> aperture -> drift in one record
         self.chunk_words = None   # 8-byte words per TMA chunk (None = lattice.DEFAULT_CHUNK_WORDS)
+        self.merge_multipoles = True  # fast encoding: co-located thin multipoles become one kick
         self._monitor_buf = None
         self.loss_tally = None
         self.last_stats = None
@@ -171,12 +172,14 @@ class Line(E.Element):
         """Host-side packed lattice (``lattice.PackedLattice``), cached."""
         if chunk_words is None:
             chunk_words = self.chunk_words
-        key = ("host", bool(strict), chunk_words, self.fuse_records, tuple(map(id, self.elements)))
+        key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles,
+               tuple(map(id, self.elements)))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
         kw = {} if chunk_words is None else {"chunk_words": chunk_words}
-        packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records, **kw)
+        packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records,
+                           merge=self.merge_multipoles, **kw)
         lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
                             packed.n_chunks, packed.n_elements, packed.flags)
         _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))
