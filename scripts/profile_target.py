@@ -7,9 +7,9 @@ sys.path.insert(0, ".")
 import xline_b200 as xl
 from xline_b200 import configs
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 151552
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 170496
 turns = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-ppt = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+ppt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 line, cols, p0c, m0 = configs.config_lhc(n)
 p = xl.Particles(p0c=p0c, mass0=m0, **cols)
 line.track(p, num_turns=turns, particles_per_thread=ppt, timed=True)

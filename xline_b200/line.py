@@ -232,6 +232,13 @@ class Line(E.Element):
             cp.beta0, cp.gamma0, cp.energy0 = p.beta0, p.gamma0, p.energy0
             if self.loss_tally is None or self.loss_tally.device != p.device:
                 self.loss_tally = torch.zeros(max(packed.n_elements, 1), dtype=torch.int64, device=p.device)
+            if particles_per_thread == 0 and (packed.flags & 2) and not strict:
+                # beam-field lattice: the thin-lens records still dominate when lenses are
+                # sparse (LHC + 74 lenses: 3 particles/thread wins); dense space-charge
+                # lattices prefer fewer particles per thread (less spilling in the field code)
+                nbf = sum(v for k, v in packed.record_counts.items() if k in (16, 17, 18))
+                sparse = nbf < 0.05 * max(sum(packed.record_counts.values()), 1)
+                particles_per_thread, threads_per_block = (3, threads_per_block or 128) if sparse else (2, threads_per_block)
             opts = _cabi.TrackOptions()
             opts.num_turns = int(num_turns)
             opts.particles_per_thread = int(particles_per_thread)
