@@ -40,8 +40,27 @@ def convert(example, out_name, synth_fort16=False):
     print(out_name, len(line), kinds, "%.1f kB" % (os.path.getsize(fn) / 1e3))
 
 
+def convert_madx(example_file, seq_name, out_name, slices, energy0_eV, mass0_eV):
+    from xline_b200.madx_input import MadxFile, makethin
+
+    mf = MadxFile(os.path.join(REF, example_file))
+    thin = makethin(mf.sequence(seq_name), slices)
+    line = Line.from_madx_sequence(thin, exact_drift=True)
+    d = line.to_dict(keepextra=True)
+    d["meta"] = dict(source="%s (MAD-X sequence %s, TEAPOT thin slicing %s, exact drifts)"
+                     % (example_file, seq_name, slices),
+                     energy0_eV=energy0_eV, mass0_eV=mass0_eV, tlen=thin.length, n_elements=len(line))
+    fn = os.path.join(OUT, out_name + ".json.gz")
+    with gzip.GzipFile(fn, "wb", mtime=0) as fh:
+        fh.write(json.dumps(d, separators=(",", ":")).encode())
+    print(out_name, len(line), "%.1f kB" % (os.path.getsize(fn) / 1e3))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    # examples/petra4/track_p1.py:21-30: 6 GeV electrons, 4 slices for sbend and quadrupole
+    convert_madx("examples/petra4/h7ba_n8.seq", "ring", "petra4", {"sbend": 4, "quadrupole": 4},
+                 6e9, 0.51099895e6)
     convert("fodo", "fodo")
     convert("lhc", "lhc", synth_fort16=True)
     convert("bbsimple", "bbsimple")

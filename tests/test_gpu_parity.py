@@ -555,3 +555,47 @@ def test_monitor_rolling_and_skip():
     assert sorted(set(store["at_turn"].ravel().tolist())) == [7, 10]
     assert np.array_equal(mon.data["at_turn"].cpu().numpy(), store["at_turn"].astype(float))
     assert np.array_equal(mon.data["x"].cpu().numpy(), store["x"])
+
+
+def test_petra4_c4_real_lattice_against_oracle():
+    """BASELINE config C4 lattice: examples/petra4/h7ba_n8.seq read without MAD-X
+    (xline_b200.madx_input), 4-slice TEAPOT thin lenses, 31 025 elements; dynamic-aperture
+    grid, 2 turns."""
+    from xline_b200 import configs
+
+    line, cols, p0c, m0 = configs.config_petra4(300, x_max=6e-3, y_max=3e-3)
+    line.append_element(__import__("xline_b200").LimitEllipse(a=8e-3, b=4e-3), "scraper")
+    p = make_particles(cols, p0c, m0)
+    line.track(p, num_turns=2)
+    got = p.to_numpy()
+    ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=2)
+    assert np.array_equal(got["state"], ref["state"]) and np.array_equal(got["at_turn"], ref["at_turn"])
+    alive = ref["state"] == 1
+    assert 0 < alive.sum()
+    for k in H.COORDS:
+        scale_ok = H.scaled_err(got[k][alive], ref[k][alive])
+        if k == "zeta":
+            # zeta of an exact drift is L*(rvv - (1+delta)/pz): a difference of two numbers of
+            # the size of the path length, so its rounding noise is absolute, ~1e-16 x the
+            # distance travelled (2 x 2301.6 m here), not relative to the (tiny) zeta spread
+            assert np.max(np.abs(got[k][alive] - ref[k][alive])) <= 5e-12, k
+            continue
+        if k == "delta":
+            # the grid beam starts at delta = 0: delta is only what the cavities add (~1e-6),
+            # and their phase sees the zeta noise above (k * 4e-13 m -> 1e-5 eV of 6 GeV)
+            assert np.max(np.abs(got[k][alive] - ref[k][alive])) <= 1e-13, k
+            continue
+        assert scale_ok <= 1e-10 or np.max(np.abs(got[k][alive] - ref[k][alive])) <= 1e-18, (k, scale_ok)
+    p2 = make_particles(cols, p0c, m0)
+    line.track(p2, num_turns=2, strict=True)
+    got2 = p2.to_numpy()
+    assert np.array_equal(got2["state"], ref["state"])
+    # strict kernel: one turn of this lattice is bit-identical to the oracle (checked on the
+    # B200); over two turns the last-ulp difference between CUDA's and glibc's sin() in the
+    # cavities reaches rvv and, through L*rvv, zeta at the 1e-15 m level
+    for k in H.COORDS:
+        e2 = H.scaled_err(got2[k][alive], ref[k][alive])
+        if k == "zeta":
+            assert np.max(np.abs(got2[k][alive] - ref[k][alive])) <= 5e-14, k
+            continue
+        assert e2 <= 1e-13 or np.max(np.abs(got2[k][alive] - ref[k][alive])) <= 1e-16, (k, e2)

@@ -205,3 +205,17 @@ def config_petra_like(n=1_000_000, rank=0, n_cells=120, grid=None):
     cols = dict(x=x0.copy(), px=np.zeros(n), y=y0.copy(), py=np.zeros(n), zeta=np.zeros(n),
                 delta=np.zeros(n))
     return Line(els, names), cols, p0c, m0
+
+
+def config_petra4(n=1_000_000, rank=0, x_max=1.5e-3, y_max=0.8e-3):
+    """C4: the PETRA IV lattice of examples/petra4/h7ba_n8.seq (4 886 placements; 2 rfcavity at
+    500 MHz), read by ``xline_b200.madx_input`` and made thin with 4 TEAPOT slices per
+    quadrupole / bend (examples/petra4/track_p1.py:26-30), exact drifts: 31 025 elements.
+    Beam: a dynamic-aperture scan, a 2-D grid of (x, y) start amplitudes."""
+    line, meta = load_lattice("petra4")
+    p0c, m0 = p0c_of(meta)
+    side = int(np.ceil(np.sqrt(n)))
+    gx, gy = np.meshgrid(np.linspace(0, x_max, side), np.linspace(0, y_max, side))
+    cols = dict(x=gx.ravel()[:n].copy(), px=np.zeros(n), y=gy.ravel()[:n].copy(), py=np.zeros(n),
+                zeta=np.zeros(n), delta=np.zeros(n))
+    return line, cols, p0c, m0

@@ -289,6 +289,20 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ loaders
     @classmethod
+    def from_madx_sequence(cls, sequence, classes=None, ignored_madtypes=(), exact_drift=False,
+                           drift_threshold=1e-6, install_apertures=False):
+        """xline/line.py:297-324 for a thin ``madx_input.MadSequence`` (or any object with
+        ``elements`` / ``element_positions()`` / ``length`` like a cpymad sequence)."""
+        from .madx_input import iter_from_madx_sequence
+
+        names, els = [], []
+        for nm, el in iter_from_madx_sequence(sequence, classes or E.element_classes(), ignored_madtypes,
+                                              exact_drift, drift_threshold, install_apertures):
+            names.append(nm)
+            els.append(el)
+        return cls(els, names)
+
+    @classmethod
     def from_sixinput(cls, sixinput, classes=None):
         """xline/line.py:279-295 with this package's SixTrack reader."""
         from .sixtrack_input import expand_struct
