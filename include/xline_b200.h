@@ -106,7 +106,10 @@ enum xlb_tag {
      merged (kn_i,ks_i) i=order..0  [hxl,hyl][length,1/length][knl0,ksl0 of K2] if curved
      [a*a,b*b][1/(a*a),1/(b*b)] if has_a1 (A1 is an ellipse)  A2 limits as above
      K1's own (kn_i,ks_i) i=k1_order..0 (re-evaluated only for particles lost at A1)        */
-  XLB_T_MERGED_BLOCK = 0xA0
+  XLB_T_MERGED_BLOCK = 0xA0,
+  /* Dipole edge followed by a drift: tag = 0xC0 | drift << 3 | exact << 4;
+     [hdr,drift_length][r21,r43]                              elements.py:538-548, 48-72   */
+  XLB_T_EDGE_BLOCK = 0xC0
 };
 
 typedef struct xlb_lattice {

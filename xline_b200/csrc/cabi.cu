@@ -487,6 +487,10 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           if (pairs < 6) return fail(XLB_ELATTICE, "bad beam-field record length");
           break;
         default: {
+          if ((tag & 0xc0) == XLB_T_EDGE_BLOCK) {
+            want = 2;
+            break;
+          }
           if ((tag & 0xe0) == XLB_T_THIN_BLOCK) {
             want = 2 + aux + 1 + ((tag & 4) ? 2 : 0) + ((tag & 3) ? 2 : 0);
             break;

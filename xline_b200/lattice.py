@@ -379,6 +379,7 @@ def _pack_thin_block(mp, idx, aper, drift, strict):
 
 
 T_MERGED_BLOCK = 0xA0  # thin-block bits | 0x20: two co-located multipoles as one (fast only)
+T_EDGE_BLOCK = 0xC0    # dipole edge -> drift
 MERGE_MAX_K1_ORDER = 4
 
 
@@ -474,6 +475,18 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
         idx, el = live[pos]
         pos += 1
         name = type(el).__name__
+        if fuse and name == "DipoleEdge" and pos < len(live) and \
+                type(live[pos][1]).__name__ in ("Drift", "DriftExact"):
+            # dipole edge -> drift in one record
+            d = live[pos][1]
+            pos += 1
+            plain = _pack_element(el, idx, strict, monitors)
+            rec = _Rec(T_EDGE_BLOCK | TB_DRIFT | (TB_DRIFT_EXACT if type(d).__name__ == "DriftExact" else 0),
+                       0, idx, d.length)
+            rec.w.extend([plain.w[1], plain.w[2]])  # r21, r43 as evaluated for the plain record
+            counts[rec.tag] = counts.get(rec.tag, 0) + 1
+            recs.append(rec.words())
+            continue
         merged = _try_merge(live, pos - 1) if (fuse and merge and not strict and name == "Multipole") else None
         if merged is not None:
             # two co-located thin multipoles (apertures in between allowed): one summed kick
