@@ -341,7 +341,9 @@ def run_b200(args):
         "algorithmic_fp64_ops_per_particle_turn": ops_per_turn,
         "kernel": "track_kernel<ppt=%d>" % args.ppt, "avg_launch_ms": per_launch_ms,
         "particle_turns_per_launch": local_done / max(launches["track"], 1),
-        "hbm_view": {"bytes_per_launch_algorithmic": 27 * 8 * n, "note": "entry/exit only: state is register-resident"},
+        "hbm_view": {"bytes_per_launch_algorithmic": 196 * n * max(1, -(-args.turns_per_launch // 5)),
+                     "note": "particle state is register-resident inside a work item; per particle and 5-turn "
+                             "item 92 B are loaded and 104 B stored"},
         "ncu": ncu_note,
     }
 

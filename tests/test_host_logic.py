@@ -243,3 +243,21 @@ def test_algorithmic_ops_match_oracle_count():
     line, _ = configs.load_lattice("lhc")
     assert line.algorithmic_ops_per_turn() == xo.algorithmic_ops(line.to_specs())
     assert abs(line.algorithmic_ops_per_turn() - 9.48e5) / 9.48e5 < 0.02
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under xline_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "xline_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+                assert "xline_oracle" not in txt and "ref_harness" not in txt, fn
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", os.path.join(ROOT, "xline_b200", "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cabi.lib()
