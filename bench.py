@@ -85,7 +85,10 @@ def cpu_step(n_per_proc, turns, procs):
     import multiprocessing as mp
 
     if _POOL is None:
+        import atexit
+
         _POOL = mp.get_context("spawn").Pool(procs)
+        atexit.register(lambda: (_POOL.close(), _POOL.join()))
         _POOL.map(_cpu_worker, [(r, 16, 1) for r in range(procs)])  # import + lattice load
     t0 = time.perf_counter()
     res = _POOL.map(_cpu_worker, [(r, n_per_proc, turns) for r in range(procs)])

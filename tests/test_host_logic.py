@@ -261,3 +261,19 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_cabi, "LIB_PATH", os.path.join(ROOT, "xline_b200", "does_not_exist.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _cabi.lib()
+
+
+def test_packed_lattice_binary_roundtrip(tmp_path):
+    line = xl.Line([xl.Drift(1.0), xl.Multipole(knl=[0, 0.1, 3.0]), xl.LimitRect(), xl.Drift(2.0),
+                    xl.BeamMonitor(num_stores=2, max_particle_id=9), xl.Cavity(voltage=1e6, frequency=4e8)])
+    pk = line.pack()
+    fn = str(tmp_path / "lattice.npz")
+    pk.save(fn)
+    back = lattice.PackedLattice.load(fn)
+    assert np.array_equal(back.words, pk.words) and back.words.dtype == np.uint64
+    assert (back.chunk_words, back.n_chunks, back.n_elements, back.flags) == (
+        pk.chunk_words, pk.n_chunks, pk.n_elements, pk.flags)
+    assert back.monitor_layout == pk.monitor_layout and back.record_counts == pk.record_counts
+    lat = _cabi.Lattice(back.words.ctypes.data, back.words.size, back.chunk_words, back.n_chunks,
+                        back.n_elements, back.flags)
+    assert _cabi.lib().xlb_lattice_validate(C.byref(lat)) == 0

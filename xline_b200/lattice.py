@@ -329,6 +329,26 @@ class PackedLattice:
     def strict(self):
         return bool(self.flags & F_STRICT)
 
+    # ---- on-disk form of the packed lattice: the chunked words plus the
+    # header fields of xlb_lattice_t; reload with PackedLattice.load and hand to the C ABI
+    def save(self, path):
+        np.savez_compressed(
+            path, words=self.words, chunk_words=self.chunk_words, n_chunks=self.n_chunks,
+            n_elements=self.n_elements, flags=self.flags, monitor_words=self.monitor_words,
+            monitor_layout=np.array([[m["element_index"], m["offset"], m["num_stores"], m["nn"]]
+                                     for m in self.monitor_layout], dtype=np.int64).reshape(-1, 4),
+            record_tags=np.array(sorted(self.record_counts), dtype=np.int64),
+            record_counts=np.array([self.record_counts[k] for k in sorted(self.record_counts)], dtype=np.int64))
+
+    @classmethod
+    def load(cls, path):
+        d = np.load(path)
+        layout = [dict(element_index=int(r[0]), offset=int(r[1]), num_stores=int(r[2]), nn=int(r[3]))
+                  for r in d["monitor_layout"]]
+        counts = {int(k): int(v) for k, v in zip(d["record_tags"], d["record_counts"])}
+        return cls(np.ascontiguousarray(d["words"], dtype=np.uint64), int(d["chunk_words"]), int(d["n_chunks"]),
+                   int(d["n_elements"]), int(d["flags"]), dict(layout=layout, words=int(d["monitor_words"])), counts)
+
     @property
     def nbytes(self):
         return int(self.words.nbytes)
