@@ -143,9 +143,10 @@ typedef struct xlb_track_options {
                                    1..4                                                    */
   int32_t threads_per_block;    /* 0 = default (128 at 3 particles/thread, else 256);
                                    multiple of 32, <= the variant's launch bound           */
-  int32_t turns_per_launch;  /* 0 = all turns in one launch; otherwise survivors are
-                                re-compacted (warp-ballot stream compaction) between
-                                launches of this many turns                              */
+  int32_t turns_per_launch;  /* > 0: survivors are re-compacted (warp-ballot stream
+                                compaction) between launches of this many turns; 0 =
+                                automatic (one launch up to 150 turns, else launches of 100
+                                turns); < 0 = all turns in one launch                      */
   int64_t *loss_tally;       /* optional [n_elements] int64 counters, incremented per
                                 element where a particle was lost (same memory space as
                                 the particle arrays)                                     */

@@ -324,7 +324,10 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   XLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int resident = std::max(1, occ) * sms;  // CTAs the device holds at once
   const int tpi = (o->turns_per_item == 0) ? 5 : o->turns_per_item;
-  const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch : o->num_turns;
+  // 0 = automatic: long jobs are cut into launches of 100 turns so that survivors get
+  // re-compacted now and then; < 0 = one launch whatever the length
+  const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch
+                  : (o->turns_per_launch == 0 && o->num_turns > 150 ? 100 : o->num_turns);
   const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 128.0);
   long long n_active = p->n;
   const int *idx = nullptr;
@@ -333,7 +336,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   if (segmented) XLB_CUDA(cudaMemsetAsync(s->n_lost, 0, sizeof(unsigned int), st));
 
   if (timed) XLB_CUDA(cudaEventRecord(s->ev0, st));
-  if (o->turns_per_launch > 0) {
+  if (o->turns_per_launch > 0 || seg < o->num_turns) {
     // particles lost in earlier calls still sit in the caller's arrays (state 0): start from
     // the compacted survivor list so they do not occupy lanes
     if ((rc = ensure_compaction_scratch(s, p->n)) != XLB_OK) return rc;
