@@ -277,3 +277,17 @@ def test_packed_lattice_binary_roundtrip(tmp_path):
     lat = _cabi.Lattice(back.words.ctypes.data, back.words.size, back.chunk_words, back.n_chunks,
                         back.n_elements, back.flags)
     assert _cabi.lib().xlb_lattice_validate(C.byref(lat)) == 0
+
+
+def test_particles_derived_longitudinal_variables():
+    d = np.array([-1e-3, 0.0, 2e-3])
+    p = xl.Particles(p0c=450e9, delta=d, zeta=[0.1, -0.2, 0.3], device="cpu")
+    e = p.energy.numpy()
+    pc = p.pc.numpy()
+    assert np.allclose(e ** 2, pc ** 2 + p.mass0 ** 2, rtol=1e-14)       # E^2 = (pc)^2 + m^2
+    assert np.allclose(p.ptau.numpy(), (e - p.energy0) / p.p0c, rtol=0, atol=1e-15)
+    beta = pc / e
+    assert np.allclose(p.rvv.numpy(), beta / p.beta0, rtol=1e-14)          # rvv = beta / beta0
+    assert np.allclose(p.tau.numpy() * p.beta0, p.sigma.numpy(), rtol=1e-15)
+    assert np.allclose(p.psigma.numpy() * p.beta0, p.ptau.numpy(), rtol=1e-15)
+    assert np.allclose(p.mass_ratio.numpy(), 1.0)

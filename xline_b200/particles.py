@@ -140,6 +140,39 @@ class Particles:
         self.rpp = 1 / opd
         self.zeta = self.zeta * (self.rvv / old)
 
+    # -- derived longitudinal variables (Pyparticles names; read-only views) -----------------------
+    @property
+    def ptau(self):
+        """(E - E0) / (p0 c)."""
+        b0 = self._beta0
+        return torch.sqrt(self._delta ** 2 + 2 * self._delta + 1 / (b0 * b0)) - 1 / b0
+
+    @property
+    def psigma(self):
+        return self.ptau / self._beta0
+
+    @property
+    def sigma(self):
+        """s - beta0 c t."""
+        return self.zeta / self.rvv
+
+    @property
+    def tau(self):
+        """s / beta0 - c t."""
+        return self.zeta / (self.rvv * self._beta0)
+
+    @property
+    def energy(self):
+        return self._energy0 + self.ptau * self._p0c
+
+    @property
+    def pc(self):
+        return (1 + self._delta) * self._p0c
+
+    @property
+    def mass_ratio(self):
+        return self.charge_ratio / self.chi
+
     # -- container behaviour -----------------------------------------------------------------
     def __len__(self):
         return int(self.x.shape[0])
