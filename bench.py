@@ -355,9 +355,11 @@ def run_b200(args):
         procs = host_cores()
         cpu_step(64, 1, procs)
         d, s = cpu_step(args.cpu_particles, 1, procs)
+        d1, s1 = _cpu_worker((0, args.cpu_particles, 1))  # one process, one core
         cpu_baseline = {"value": d / s, "unit": UNIT, "cores": procs, "kind": "port",
                         "sample": "%d processes x %d particles x 1 turn, same C2 lattice and beam recipe"
-                                  % (procs, args.cpu_particles)}
+                                  % (procs, args.cpu_particles),
+                        "single_core_value": d1 / s1}
 
     line_out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

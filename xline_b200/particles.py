@@ -23,6 +23,29 @@ def _default_device():
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
 
+class MathlibDefault:
+    """The reference's math seam (``xline/mathlibs.py:5-18``): elements reach NumPy/SciPy only
+    through ``p._m``.  Irrelevant on the device; kept on the host container so code written
+    against ``p._m`` keeps working."""
+
+    from numpy import sqrt, exp, sin, cos, abs, pi, tan, interp, linspace  # noqa: A004
+    from numpy import power as pow  # noqa: A004
+
+    @classmethod
+    def wfun(cls, z_re, z_im):
+        from scipy.special import wofz
+
+        w = wofz(z_re + 1j * z_im)
+        return w.real, w.imag
+
+    @classmethod
+    def gamma(cls, arg):
+        from scipy.special import gamma as tgamma
+
+        assert arg > 0.0
+        return tgamma(arg)
+
+
 class Particles:
     """``Particles(p0c=..., x=..., px=..., ...)``; scalars broadcast to the longest array.
 
@@ -31,6 +54,8 @@ class Particles:
     device; a CPU-resident container can be built for host-side work (packing, sharding,
     I/O) but ``Line.track`` refuses it -- there is no CPU tracking path in this package.
     """
+
+    _m = MathlibDefault
 
     def __init__(self, p0c=1e9, mass0=PROTON_MASS_EV, q0=1.0, n=None, device=None, pinned=False,
                  **cols):
