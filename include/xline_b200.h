@@ -159,6 +159,12 @@ typedef struct xlb_track_options {
                                 holds at once, runs persistent CTAs that pull (particle block,
                                 turn segment) items.  0 = default (5), < 0 = off          */
   int32_t reserved;
+  double *trace;             /* optional element-by-element trace, [n_elements][6][trace_particles]
+                                fp64 (x px y py zeta delta after every element for the first
+                                trace_particles particle slots; the device form of
+                                Line.track_elem_by_elem, xline/line.py:97-108).  Needs
+                                num_turns == 1 and a lattice packed without record fusing     */
+  int64_t trace_particles;
 } xlb_track_options_t;
 
 /* Statistics of the last xlb_track_* call on this thread. */

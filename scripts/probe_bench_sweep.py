@@ -10,7 +10,7 @@ from xline_b200 import configs
 n, turns = 1_000_000, 40
 line, cols, p0c, m0 = configs.config_lhc(n)
 ALL = ((2, 256, 5), (2, 256, 2), (2, 256, 10), (2, 256, -1), (3, 128, 5), (4, 128, 5), (2, 128, 5), (1, 512, 5),
-       (3, 128, -1), (1, 512, -1), (1, 256, 5), (1, 128, 5), (3, 128, 3), (3, 128, 10), (3, 96, 5), (4, 128, 5), (3, 64, 5))
+       (3, 128, -1), (1, 512, -1), (1, 256, 5), (1, 128, 5), (3, 128, 3), (3, 128, 10), (3, 96, 5), (4, 128, 5), (3, 64, 5), (3, 192, 5), (3, 160, 5))
 sel = [ALL[int(a)] for a in sys.argv[1:] if not a.startswith("cw=")] or ALL
 for a in sys.argv[1:]:
     if a.startswith("cw="):

@@ -599,3 +599,58 @@ def test_petra4_c4_real_lattice_against_oracle():
             assert np.max(np.abs(got2[k][alive] - ref[k][alive])) <= 5e-14, k
             continue
         assert e2 <= 1e-13 or np.max(np.abs(got2[k][alive] - ref[k][alive])) <= 1e-16, (k, e2)
+
+
+def test_trace_elem_by_elem_matches_oracle_element_by_element():
+    """Device element-by-element trace (xline/line.py:97-108) against the oracle stepping the
+    same line one element at a time -- the replay examples/lhc/benchmark.py:28-48 does against
+    SixTrack dumps."""
+    from oracle import xline_oracle as xo
+
+    m, specs, cols, _ = H.load_case("line_mixed_3turns")
+    line = build_line(specs)
+    n = len(cols["x"])
+    for strict in (True, False):
+        p = make_particles(cols, m["p0c"], m["mass0"])
+        trace = line.trace_elem_by_elem(p, strict=strict).cpu().numpy()
+        assert trace.shape == (len(line) + 1, 6, n)
+        o = xo.OracleParticles(n, p0c=m["p0c"], mass0=m["mass0"], **cols)
+        for f, k in enumerate(H.COORDS):
+            assert np.array_equal(trace[0, f], cols[k])
+        for i, (name, fld) in enumerate(specs):
+            rec = xo.TRACKERS[name](o, fld)
+            alive_ids = o.particle_id
+            row = trace[i + 1]
+            gone = np.ones(n, dtype=bool)
+            gone[alive_ids] = False
+            assert np.isnan(row[:, gone]).all(), (i, name)          # lost: no more rows written
+            for f, k in enumerate(H.COORDS):
+                got, want = row[f, alive_ids], getattr(o, k)
+                if strict and name not in ("Cavity", "RFMultipole"):
+                    err = np.max(np.abs(got - want)) if len(want) else 0.0
+                    assert err <= 4e-16 * max(np.max(np.abs(want)), 1e-300) * 8 or np.array_equal(got, want), (i, name, k)
+                else:
+                    assert H.rel_err(got, want) <= 1e-12 or np.max(np.abs(got - want)) <= 1e-18, (i, name, k)
+        # the particles themselves ended where a normal one-turn track puts them
+        q = make_particles(cols, m["p0c"], m["mass0"])
+        line.track(q, num_turns=1, strict=strict)
+        a, b = p.to_numpy(), q.to_numpy()
+        for k in ("state", "at_element", "at_turn"):
+            assert np.array_equal(a[k], b[k])
+
+
+def test_trace_on_lhc_first_particles():
+    from xline_b200 import configs
+
+    line, cols, p0c, m0 = configs.config_lhc(2000)
+    p = make_particles(cols, p0c, m0)
+    trace = line.trace_elem_by_elem(p, max_particles=8)
+    assert trace.shape == (len(line) + 1, 6, 8)
+    last = trace[-1].cpu().numpy()
+    q = make_particles(cols, p0c, m0)
+    line.merge_multipoles = False
+    line.track(q, num_turns=1)
+    ref = q.to_numpy()
+    alive = ref["state"][:8] == 1
+    for f, k in enumerate(H.COORDS):
+        assert np.array_equal(last[f][alive], ref[k][:8][alive]), k   # same maps, element by element

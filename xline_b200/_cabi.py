@@ -44,6 +44,7 @@ class TrackOptions(C.Structure):
         ("threads_per_block", C.c_int32), ("turns_per_launch", C.c_int32),
         ("loss_tally", C.c_void_p), ("monitor_data", C.c_void_p), ("monitor_words", C.c_int64),
         ("compact_threshold", C.c_double), ("turns_per_item", C.c_int32), ("reserved", C.c_int32),
+        ("trace", C.c_void_p), ("trace_particles", C.c_int64),
     ]
 
 

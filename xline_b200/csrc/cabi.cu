@@ -219,7 +219,7 @@ static int compact_alive(const long long *state, long long n, int *idx_out, int 
 // ------------------------------------------------------------------ variant selection
 // Among the variants of the requested particles-per-thread, the one with the smallest
 // launch-bounds ceiling that still admits `threads` (tighter ceilings allow more registers).
-static const Variant *pick_variant(bool strict, bool beamfields, int ppt, int threads) {
+static const Variant *pick_variant(bool strict, bool beamfields, int ppt, int threads, bool trace) {
   int n = 0;
   const Variant *tab;
   if (strict)
@@ -229,6 +229,11 @@ static const Variant *pick_variant(bool strict, bool beamfields, int ppt, int th
   const Variant *best = nullptr;
   for (int i = 0; i < n; ++i) {
     const Variant &v = tab[i];
+    if (trace) {
+      if (v.trace) return &v;
+      continue;
+    }
+    if (v.trace) continue;
     if (!best) { best = &v; continue; }
     const int dv = std::abs(v.ppt - ppt), db = std::abs(best->ppt - ppt);
     if (dv < db) { best = &v; continue; }
@@ -284,9 +289,13 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread
                                                   : ((strict || beamfields) ? 2 : 3);
   const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (ppt_req == 3 ? 128 : 256);
-  const Variant *v = pick_variant(strict, beamfields, ppt_req, threads_req);
+  const bool trace = o->trace != nullptr;
+  if (trace && (o->num_turns != 1 || o->trace_particles < 1))
+    return fail(XLB_EINVAL, "element-by-element trace needs num_turns == 1 and trace_particles >= 1");
+  const Variant *v = pick_variant(strict, beamfields, ppt_req, threads_req, trace);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
-  int threads = o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req);
+  int threads = trace ? v->threads
+                      : (o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req));
   if (threads % 32 || threads > v->threads)
     return fail(XLB_EINVAL, "threads_per_block must be a multiple of 32 and <= the variant's limit");
 
@@ -316,6 +325,8 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.mon = o->monitor_data;
   a.mon_words = o->monitor_words;
   a.n_lost = s->n_lost;
+  a.trace = o->trace;
+  a.trace_n = o->trace_particles;
 
   int occ = 1;
   XLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, threads, smem));

@@ -29,11 +29,14 @@ struct KArgs {
   unsigned int *queue;
   unsigned int n_blocks, n_items;
   int turns_per_item;
+  // element-by-element trace (debug kernels only): [n_elements][6][trace_n] fp64
+  double *trace;
+  long long trace_n;
 };
 
 struct Variant {
   const char *name;
-  int strict, beamfields, ppt, threads;
+  int strict, beamfields, ppt, threads, trace;
   const void *func;
   void (*launch)(const KArgs &, int blocks, int threads, size_t smem, void *stream);
 };

@@ -13,6 +13,7 @@
 
 namespace xlb {
 using namespace XLB_NS;
+XLB_DEF_TRACE_VARIANT()
 #if XLB_BEAMFIELDS
 // Same launch bounds as the lean kernels: the thin-lens records dominate even a beam-beam
 // lattice (74 lenses among 5 500 records on C3), so the register budget is set by them and
@@ -24,6 +25,7 @@ static const Variant fast_bf_table[] = {
     XLB_VARIANT_ENTRY("fast/ppt1/t256/beamfields", 1, 256, 2),
     XLB_VARIANT_ENTRY("fast/ppt2/t256/beamfields", 2, 256, 2),
     XLB_VARIANT_ENTRY("fast/ppt3/t128/beamfields", 3, 128, 3),
+    XLB_TRACE_ENTRY("fast/trace"),
 };
 const Variant *fast_bf_variants(int *n) {
   *n = static_cast<int>(sizeof(fast_bf_table) / sizeof(fast_bf_table[0]));
@@ -55,6 +57,7 @@ static const Variant XLB_TABLE[] = {
     XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_SUFFIX, 2, 256, 2),
     XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 3),
     XLB_VARIANT_ENTRY("fast/ppt4/t128" XLB_SUFFIX, 4, 128, 2),
+    XLB_TRACE_ENTRY("fast/trace"),
 };
 const Variant *XLB_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));

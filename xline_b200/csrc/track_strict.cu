@@ -15,6 +15,7 @@
 
 namespace xlb {
 using namespace XLB_NS;
+XLB_DEF_TRACE_VARIANT()
 XLB_DEF_VARIANT(1, 256, 1)
 XLB_DEF_VARIANT(2, 256, 1)
 
@@ -30,6 +31,7 @@ XLB_DEF_VARIANT(2, 256, 1)
 static const Variant XLB_TABLE[] = {
     XLB_VARIANT_ENTRY("strict/ppt1" XLB_SUFFIX, 1, 256, 1),
     XLB_VARIANT_ENTRY("strict/ppt2" XLB_SUFFIX, 2, 256, 1),
+    XLB_TRACE_ENTRY("strict/trace"),
 };
 const Variant *XLB_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(XLB_TABLE) / sizeof(XLB_TABLE[0]));

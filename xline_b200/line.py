@@ -173,13 +173,14 @@ class Line(E.Element):
         if chunk_words is None:
             chunk_words = self.chunk_words
         key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles,
-               tuple(map(id, self.elements)))
+               getattr(self, "_keep_noops", False), tuple(map(id, self.elements)))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
         kw = {} if chunk_words is None else {"chunk_words": chunk_words}
         packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records,
-                           merge=self.merge_multipoles, **kw)
+                           merge=self.merge_multipoles,
+                           drop_noops=not getattr(self, "_keep_noops", False), **kw)
         lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
                             packed.n_chunks, packed.n_elements, packed.flags)
         _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))
@@ -198,7 +199,7 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ the hot path
     def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
-              threads_per_block=0, timed=False, turns_per_item=0):
+              threads_per_block=0, timed=False, turns_per_item=0, _trace=None):
         """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
         times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
         returns ``None`` like the reference.
@@ -245,6 +246,9 @@ class Line(E.Element):
             opts.threads_per_block = int(threads_per_block)
             opts.turns_per_launch = int(turns_per_launch)
             opts.turns_per_item = int(turns_per_item)
+            if _trace is not None:
+                opts.trace = _trace.data_ptr()
+                opts.trace_particles = int(_trace.shape[2])
             opts.loss_tally = self.loss_tally.data_ptr()
             if packed.monitor_words > 0:
                 if self._monitor_buf is None or self._monitor_buf.device != p.device:
@@ -273,6 +277,28 @@ class Line(E.Element):
     def reset_monitors(self):
         if self._monitor_buf is not None:
             self._monitor_buf.fill_(float("nan"))
+
+    def trace_elem_by_elem(self, p, max_particles=None, strict=False):
+        """Device form of ``track_elem_by_elem`` (xline/line.py:97-108): one pass over the line
+        with the debug kernel, returning a tensor ``[len(self) + 1, 6, K]`` -- row 0 the
+        starting coordinates, row ``i + 1`` the coordinates (x, px, y, py, zeta, delta) of the
+        first ``K = max_particles`` particles after element ``i``; NaN from the element where
+        a particle was lost.  ``p`` is tracked in place.  The line is packed element by element
+        (no record fusing, no merging, no-ops kept) so every element owns a row."""
+        n = len(p)
+        k = n if max_particles is None else min(int(max_particles), n)
+        saved = (self.fuse_records, self.merge_multipoles, self._cache)
+        self.fuse_records, self.merge_multipoles, self._cache = False, False, {}
+        self._keep_noops = True
+        try:
+            trace = torch.full((len(self) + 1, 6, k), float("nan"), dtype=torch.float64, device=p.device)
+            for f, name in enumerate(("x", "px", "y", "py", "zeta", "delta")):
+                trace[0, f] = getattr(p, name)[:k]
+            self.track(p, num_turns=1, strict=strict, _trace=trace[1:])
+        finally:
+            self._keep_noops = False
+            self.fuse_records, self.merge_multipoles, self._cache = saved
+        return trace
 
     def track_elem_by_elem(self, p, start=True, end=False):
         """Debug path (xline/line.py:97-108): one single-element launch per element,
