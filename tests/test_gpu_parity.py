@@ -654,3 +654,55 @@ def test_trace_on_lhc_first_particles():
     alive = ref["state"][:8] == 1
     for f, k in enumerate(H.COORDS):
         assert np.array_equal(last[f][alive], ref[k][:8][alive]), k   # same maps, element by element
+
+
+def test_full_size_c2_schedule_invariance():
+    """BASELINE C2 at its full particle count (1 M): the production schedule (persistent CTAs,
+    work queue, automatic segmentation with survivor compaction) gives bit-identical particles
+    to one plain launch -- the result cannot depend on how the work was cut."""
+    from xline_b200 import configs
+
+    n, turns = 1_000_000, 12
+    line, cols, p0c, m0 = configs.config_lhc(n)
+    p1 = make_particles(cols, p0c, m0)
+    line.track(p1, num_turns=turns, turns_per_launch=4)            # queue + 3 launches + compaction
+    t1 = line.loss_tally.clone()
+    line.loss_tally.zero_()
+    p2 = make_particles(cols, p0c, m0)
+    line.track(p2, num_turns=turns, turns_per_launch=-1, turns_per_item=-1)   # one plain launch
+    assert torch.equal(t1, line.loss_tally)
+    lost = int((p1.state == 0).sum())
+    assert 0 < lost < n and int(t1.sum()) == lost
+    for k, a in p1._columns():
+        b = dict(p2._columns())[k]
+        if k == "s":
+            assert torch.allclose(a, b, rtol=1e-11, atol=0)
+        else:
+            assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), k
+    assert int(p1.at_turn.sum()) == int(p2.at_turn.sum())
+
+
+def test_inverse_elements_return_to_start():
+    """Domain property at size: every thin map followed by its inverse restores the beam
+    (drifts exactly in x, y up to rounding; kicks to 1 ulp of the kick)."""
+    import xline_b200 as xl
+
+    n = 500_000
+    rng = np.random.default_rng(9)
+    cols = dict(x=rng.normal(0, 1e-3, n), px=rng.normal(0, 1e-4, n), y=rng.normal(0, 1e-3, n),
+                py=rng.normal(0, 1e-4, n), zeta=rng.normal(0, 0.05, n), delta=rng.normal(0, 3e-4, n))
+    knl, ksl = [1e-4, 0.02, 1.5, 30.0], [0.0, 0.01, -0.7]
+    line = xl.Line([
+        xl.Drift(length=3.7), xl.Drift(length=-3.7),
+        xl.Multipole(knl=knl, ksl=ksl), xl.Multipole(knl=[-k for k in knl], ksl=[-k for k in ksl]),
+        xl.XYShift(dx=1e-4, dy=-2e-4), xl.XYShift(dx=-1e-4, dy=2e-4),
+        xl.SRotation(angle=23.0), xl.SRotation(angle=-23.0),
+        xl.DipoleEdge(h=0.01, e1=0.1), xl.DipoleEdge(h=-0.01, e1=0.1),
+    ])
+    line.merge_multipoles = False
+    p = make_particles(cols, 7e12, 938.27208816e6)
+    line.track(p, num_turns=3)
+    got = p.to_numpy()
+    for k in H.COORDS:  # a few ulp of the beam size after 3 x 10 maps
+        assert np.max(np.abs(got[k] - cols[k])) <= 1e-14 * np.max(np.abs(cols[k])), k
+    assert np.array_equal(got["delta"], cols["delta"])
