@@ -291,3 +291,67 @@ def test_particles_derived_longitudinal_variables():
     assert np.allclose(p.tau.numpy() * p.beta0, p.sigma.numpy(), rtol=1e-15)
     assert np.allclose(p.psigma.numpy() * p.beta0, p.ptau.numpy(), rtol=1e-15)
     assert np.allclose(p.mass_ratio.numpy(), 1.0)
+
+
+def test_line_like_reference_test_line():
+    """reference tests/test_line.py:7-94, line for line."""
+    rfmultipole = xl.RFMultipole(frequency=100, knl=[0.1, 0.2], ksl=[0.3, 0.4])
+    zero_drift = xl.Drift(0)
+    line = xl.Line(elements=[zero_drift, rfmultipole, zero_drift],
+                   element_names=["zero_drift", "rfmultipole", "zero_drift"])
+    length = 1.4
+    n_elements, position = 3, 1
+    line.insert_element(position, xl.DriftExact(length), "exact drift")
+    n_elements += 1
+    assert len(line) == n_elements and line.find_element_ids("exact drift")[0] == position
+    assert line.get_length() == length
+    line.insert_element(position, xl.Multipole(knl=[0.1]), "multipole")
+    line.insert_element(position + 1, xl.LimitEllipse(a=0.08, b=0.02), "multipole_aperture")
+    n_elements += 2
+    assert len(line) == n_elements
+    for kw in (dict(dx=0, dy=0), dict(dx=0.2, dy=-0.003)):
+        line._add_offset_error_to("multipole", **kw)
+        n_elements += 2
+        assert len(line) == n_elements
+    for angle in (0, 0.1):
+        line._add_tilt_error_to("multipole", angle=angle)
+        n_elements += 2
+        assert len(line) == n_elements
+    line._add_multipole_error_to("multipole", knl=[0, 0.1], ksl=[-0.03, 0.01])
+    mp = line.elements[line.element_names.index("multipole")]
+    assert mp.knl == [0.1, 0.1] and mp.ksl == [-0.03, 0.01]
+    # wrappers sit outside the element AND its aperture
+    i0, i1 = line.find_element_ids("multipole")
+    assert line.element_names[i0 - 1] == "multipole_tilt_in" and line.element_names[i1] == "multipole_tilt_out"
+    line_dict = line.to_dict()
+    line = xl.Line.from_dict(line_dict)
+    assert len(line) == n_elements
+    line.append_line(xl.Line.from_dict(line_dict))
+    n_elements *= 2
+    assert len(line) == n_elements and line.get_length() == 2 * length
+    sd, su = line.get_s_elements("downstream"), line.get_s_elements("upstream")
+    assert max(np.array(sd) - np.array(su)) == length
+    line.insert_element(1, xl.Multipole(), "inactive_multipole")
+    n_elements += 1
+    assert len(line.remove_inactive_multipoles()) == n_elements - 1 and len(line) == n_elements
+    line.remove_inactive_multipoles(inplace=True)
+    n_elements -= 1
+    assert len(line) == n_elements
+    assert len(line.merge_consecutive_drifts()) == n_elements - 1
+    line.merge_consecutive_drifts(inplace=True)
+    n_elements -= 1
+    assert len(line) == n_elements
+    assert len(line.get_elements_of_type(xl.Drift)) == 2
+    drifts = line.get_elements_of_type(xl.Drift)[0]
+    nz = len([d for d in drifts if d.length == 0])
+    assert len(line.remove_zero_length_drifts()) == n_elements - nz
+    line.remove_zero_length_drifts(inplace=True)
+    assert len(line) == n_elements - nz
+    # reference tests/test_line.py:97-105 (isthick attribute)
+    thick = xl.Multipole(knl=[0, -1.0], ksl=[0, 0], length=4)
+    thick.isthick = True
+    line2 = xl.Line(elements=[xl.Drift(length=1.0), xl.Multipole(knl=[0, 1.0], ksl=[0, 0]), xl.Drift(length=3), thick])
+    assert np.isclose(line2.get_length(), 8.0, rtol=1e-30, atol=1e-20)
+    merged = xl.Line([xl.Multipole(knl=[0, 1.0]), xl.Multipole(knl=[1e-3, 0.5, 2.0], ksl=[0, 0.1])]).merge_consecutive_multipoles()
+    assert len(merged) == 1 and merged.elements[0].knl == [1e-3, 1.5, 2.0] and merged.elements[0].ksl == [0, 0.1, 0]
+    assert line2.get_element_ids_of_type(xl.Drift, start_idx_offset=2) == [2, 4]

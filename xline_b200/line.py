@@ -16,6 +16,12 @@ from . import elements as E
 from .lattice import MONITOR_FIELDS, algorithmic_ops, element_specs, pack_line
 
 _thick = (E.Drift, E.DriftExact)
+deg2rad = np.pi / 180.0
+
+
+def _is_thick(element):
+    """xline/line.py:12-14."""
+    return bool(getattr(element, "isthick", False)) or isinstance(element, _thick)
 
 
 class Line(E.Element):
@@ -105,7 +111,7 @@ class Line(E.Element):
         return self
 
     def get_length(self):  # xline/line.py:122-130
-        return sum(el.length for el in self.elements if isinstance(el, _thick))
+        return sum(el.length for el in self.elements if _is_thick(el))
 
     def get_s_elements(self, mode="upstream"):  # xline/line.py:132-144
         assert mode in ("upstream", "downstream")
@@ -113,7 +119,7 @@ class Line(E.Element):
         for el in self.elements:
             if mode == "upstream":
                 out.append(s)
-            if isinstance(el, _thick):
+            if _is_thick(el):
                 s += el.length
             if mode == "downstream":
                 out.append(s)
@@ -146,14 +152,88 @@ class Line(E.Element):
     def merge_consecutive_drifts(self, inplace=False):  # xline/line.py:186-211
         els, names = [], []
         for el, nm in zip(self.elements, self.element_names):
-            if els and type(el) is type(els[-1]) and isinstance(el, _thick):
-                els[-1] = type(el)(length=els[-1].length + el.length)
+            if els and isinstance(el, _thick) and isinstance(els[-1], _thick):
+                els[-1] = type(els[-1])(length=els[-1].length + el.length)  # keeps the first one's kind
                 names[-1] = names[-1] + "_" + nm
             else:
                 els.append(el.copy() if isinstance(el, _thick) else el)
                 names.append(nm)
         new = Line(els, names)
         return self._adopt(new) if inplace else new
+
+    def merge_consecutive_multipoles(self, inplace=False):  # xline/line.py:213-251
+        els, names = [], []
+        for el, nm in zip(self.elements, self.element_names):
+            prev = els[-1] if els else None
+            if (isinstance(el, E.Multipole) and isinstance(prev, E.Multipole)
+                    and prev.hxl == el.hxl and prev.hyl == el.hyl):
+                n = max(len(prev.knl), len(prev.ksl), len(el.knl), len(el.ksl))
+                knl, ksl = np.zeros(n), np.zeros(n)
+                for src in (prev, el):
+                    knl[: len(src.knl)] += np.asarray(src.knl, dtype=float)
+                    ksl[: len(src.ksl)] += np.asarray(src.ksl, dtype=float)
+                els[-1] = E.Multipole(knl=list(knl), ksl=list(ksl), hxl=prev.hxl, hyl=prev.hyl,
+                                      length=prev.length)
+                names[-1] = names[-1] + "_" + nm
+            else:
+                els.append(el)
+                names.append(nm)
+        new = Line(els, names)
+        return self._adopt(new) if inplace else new
+
+    def get_element_ids_of_type(self, types, start_idx_offset=0):  # xline/line.py:270-282
+        assert start_idx_offset >= 0
+        types = tuple(types) if hasattr(types, "__iter__") else (types,)
+        return [i + start_idx_offset for i, el in enumerate(self.elements) if isinstance(el, types)]
+
+    # ---- error handling (alignment, multipole errors): xline/line.py:328-415 ------------
+    def find_element_ids(self, element_name):
+        """Index of the element and the index just after it, any ``<name>_aperture`` element
+        that follows included (xline/line.py:330-348)."""
+        idx_el = self.element_names.index(element_name)
+        try:
+            idx_after = self.element_names.index(element_name + "_aperture") + 1
+        except ValueError:
+            idx_after = idx_el + 1
+        return idx_el, idx_after
+
+    def _add_offset_error_to(self, element_name, dx=0, dy=0):  # xline/line.py:350-358
+        idx_el, idx_after = self.find_element_ids(element_name)
+        self.insert_element(idx_el, E.XYShift(dx=dx, dy=dy), element_name + "_offset_in")
+        self.insert_element(idx_after + 1, E.XYShift(dx=-dx, dy=-dy), element_name + "_offset_out")
+
+    def _add_aperture_offset_error_to(self, element_name, arex=0, arey=0):  # xline/line.py:360-373
+        idx_el, idx_after = self.find_element_ids(element_name)
+        idx_aper = idx_after - 1
+        if self.element_names[idx_aper] != element_name + "_aperture":
+            print("Info: Element", element_name, ": arex/y provided without aperture -> arex/y ignored")
+            return
+        self.insert_element(idx_aper, E.XYShift(dx=arex, dy=arey), element_name + "_aperture_offset_in")
+        self.insert_element(idx_after + 1, E.XYShift(dx=-arex, dy=-arey),
+                            element_name + "_aperture_offset_out")
+
+    def _add_tilt_error_to(self, element_name, angle):  # xline/line.py:375-400 (angle in degrees)
+        idx_el, idx_after = self.find_element_ids(element_name)
+        element = self.elements[idx_el]
+        if isinstance(element, E.Multipole) and (element.hxl or element.hyl):
+            dpsi = angle * deg2rad
+            hxl0, hyl0 = element.hxl, element.hyl
+            element.hxl = hxl0 * np.cos(dpsi) - hyl0 * np.sin(dpsi)
+            element.hyl = hxl0 * np.sin(dpsi) + hyl0 * np.cos(dpsi)
+        self.insert_element(idx_el, E.SRotation(angle=angle), element_name + "_tilt_in")
+        self.insert_element(idx_after + 1, E.SRotation(angle=-angle), element_name + "_tilt_out")
+
+    def _add_multipole_error_to(self, element_name, knl=(), ksl=()):  # xline/line.py:402-415
+        assert element_name in self.element_names
+        element = self.elements[self.element_names.index(element_name)]
+        for attr, extra in (("knl", knl), ("ksl", ksl)):
+            extra = np.trim_zeros(np.asarray(extra, dtype=float), trim="b")
+            cur = list(getattr(element, attr))
+            cur += [0] * (len(extra) - len(cur))
+            for i, c in enumerate(extra):
+                cur[i] += c
+            setattr(element, attr, cur)
+        self.invalidate()
 
     def _adopt(self, other):
         self.elements, self.element_names = other.elements, other.element_names
