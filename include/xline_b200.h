@@ -215,6 +215,10 @@ int xlb_compact_alive_device(const int64_t *state, int64_t n, int32_t *idx_out,
  * denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry). */
 int xlb_measure_fp64_peak(int repeats, double *flops_out, double *ms_out);
 
+/* Single-warp DFMA timing: cycles per DFMA with 1, 2, 4 and 8 independent dependent chains
+ * (cycles_per_dfma[0..3]); the first is the dependent-issue latency of the FP64 pipe. */
+int xlb_measure_dfma_latency(double *cycles_per_dfma, int n);
+
 /* Number of tracking-kernel variants compiled in, and a description of variant i
  * ("fast/ppt2/lean", ...) with its register count -- build introspection for tests. */
 int xlb_kernel_variant_count(void);

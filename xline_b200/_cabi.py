@@ -14,7 +14,8 @@ ABI_VERSION = 1
 EXPORTS = (
     "xlb_abi_version", "xlb_last_error", "xlb_lattice_validate", "xlb_track_device",
     "xlb_track_device_timed", "xlb_track_host", "xlb_get_stats", "xlb_compact_alive_device",
-    "xlb_measure_fp64_peak", "xlb_kernel_variant_count", "xlb_kernel_variant_info",
+    "xlb_measure_fp64_peak", "xlb_measure_dfma_latency", "xlb_kernel_variant_count",
+    "xlb_kernel_variant_info",
 )
 
 
@@ -112,6 +113,15 @@ def kernel_variants():
         check(L.xlb_kernel_variant_info(i, buf, 64, C.byref(regs), C.byref(thr)))
         out.append(dict(name=buf.value.decode(), regs=regs.value, max_threads=thr.value))
     return out
+
+
+def measure_dfma_latency():
+    """Cycles per DFMA of one warp running 1, 2, 4, 8 independent chains."""
+    out = (C.c_double * 4)()
+    L = lib()
+    L.xlb_measure_dfma_latency.argtypes = [C.POINTER(C.c_double), C.c_int]
+    check(L.xlb_measure_dfma_latency(out, 4))
+    return dict(zip((1, 2, 4, 8), [float(v) for v in out]))
 
 
 def measure_fp64_peak(repeats=5):

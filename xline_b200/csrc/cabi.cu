@@ -440,6 +440,37 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
   if (t == 123.456) out[0] = t;  // keep the chains alive
 }
 
+// One warp, CHAINS independent dependent-DFMA chains: cycles per DFMA (clock64).  CHAINS = 1
+// gives the dependent-issue latency, larger CHAINS the single-warp throughput.
+template <int CHAINS>
+__global__ void dfma_latency_kernel(double *out, long long *cycles, int iters, double a, double b) {
+  double acc[CHAINS];
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) acc[c] = threadIdx.x * 1e-3 + c;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) acc[c] = fma(acc[c], a, b);
+  }
+  const long long t1 = clock64();
+  double t = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) t += acc[c];
+  if (threadIdx.x == 0) *cycles = t1 - t0;
+  if (t == 123.456) out[0] = t;
+}
+
+template <int CHAINS>
+static int run_latency(double *d, long long *dc, double *cyc_per_dfma) {
+  const int iters = 1 << 14;
+  dfma_latency_kernel<CHAINS><<<1, 32>>>(d, dc, iters, 1.0000001, 1e-9);
+  dfma_latency_kernel<CHAINS><<<1, 32>>>(d, dc, iters, 1.0000001, 1e-9);
+  long long h = 0;
+  XLB_CUDA(cudaMemcpy(&h, dc, sizeof(h), cudaMemcpyDeviceToHost));
+  *cyc_per_dfma = static_cast<double>(h) / (static_cast<double>(iters) * CHAINS);
+  return XLB_OK;
+}
+
 }  // namespace xlb
 
 using namespace xlb;
@@ -687,6 +718,21 @@ int xlb_measure_fp64_peak(int repeats, double *flops_out, double *ms_out) {
   *flops_out = flops / (best * 1e-3);
   if (ms_out) *ms_out = best;
   return XLB_OK;
+}
+
+int xlb_measure_dfma_latency(double *cycles_per_dfma, int n) {
+  if (!cycles_per_dfma || n < 4) return fail(XLB_EINVAL, "need room for 4 results");
+  double *d = nullptr;
+  long long *dc = nullptr;
+  XLB_CUDA(cudaMalloc(&d, 64));
+  XLB_CUDA(cudaMalloc(&dc, 8));
+  int rc = run_latency<1>(d, dc, &cycles_per_dfma[0]);
+  if (rc == XLB_OK) rc = run_latency<2>(d, dc, &cycles_per_dfma[1]);
+  if (rc == XLB_OK) rc = run_latency<4>(d, dc, &cycles_per_dfma[2]);
+  if (rc == XLB_OK) rc = run_latency<8>(d, dc, &cycles_per_dfma[3]);
+  cudaFree(d);
+  cudaFree(dc);
+  return rc;
 }
 
 int xlb_kernel_variant_count(void) {
