@@ -64,9 +64,7 @@ def _compile(unit, verbose):
 
 
 def _units():
-    if os.path.exists(os.path.join(CSRC, "beamfields.cuh")):
-        return list(UNITS)
-    return [u for u in UNITS if not u[0].endswith("_bf")] + [("bf_stub", "bf_stub.cu", [])]
+    return list(UNITS)
 
 
 def build(force=False, verbose=False):
