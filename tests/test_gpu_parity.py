@@ -706,3 +706,29 @@ def test_inverse_elements_return_to_start():
     for k in H.COORDS:  # a few ulp of the beam size after 3 x 10 maps
         assert np.max(np.abs(got[k] - cols[k])) <= 1e-14 * np.max(np.abs(cols[k])), k
     assert np.array_equal(got["delta"], cols["delta"])
+
+
+def test_work_queue_with_strict_kernel_and_monitor():
+    """The queue schedule with the strict kernel and a BeamMonitor in the line: monitor slots,
+    turn bookkeeping and particles identical to the plain launch."""
+    import xline_b200 as xl
+    from xline_b200 import configs
+
+    n, turns = 160_000, 7
+    base, cols, p0c, m0 = configs.config_fodo(n)
+    mon = xl.BeamMonitor(num_stores=turns, start=0, skip=1, min_particle_id=100, max_particle_id=1123)
+    els = list(base.elements) + [xl.LimitEllipse(a=3.5e-3, b=3.5e-3), mon]
+    outs = []
+    for tpi in (-1, 2):
+        line = xl.Line(els)
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=turns, strict=True, turns_per_item=tpi, particles_per_thread=1,
+                   threads_per_block=128)
+        outs.append((p.to_numpy(), {k: v.clone() for k, v in mon.data.items()}))
+    (a, ma), (b, mb) = outs
+    assert 0 < (a["state"] == 0).sum() < n
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    for k in ma:
+        assert torch.equal(torch.nan_to_num(ma[k], nan=-7.0), torch.nan_to_num(mb[k], nan=-7.0)), k
+    assert int((~torch.isnan(ma["x"])).sum()) > 1000

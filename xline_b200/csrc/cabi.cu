@@ -604,6 +604,7 @@ int xlb_track_host(const xlb_lattice_t *hl, xlb_particles_t *hp, const xlb_track
   if ((rc = check_particles(hp)) != XLB_OK) return rc;
   if (!o) return fail(XLB_EINVAL, "options is null");
   if ((rc = xlb_lattice_validate(hl)) != XLB_OK) return rc;
+  if (o->trace) return fail(XLB_EINVAL, "element-by-element trace is a device-entry-point feature");
   const long long n = hp->n;
   if (n == 0 || o->num_turns == 0) return XLB_OK;
   Scratch *s = nullptr;
