@@ -207,6 +207,119 @@ def config_petra_like(n=1_000_000, rank=0, n_cells=120, grid=None):
     return Line(els, names), cols, p0c, m0
 
 
+def install_spacecharge(line, n_kicks, p0c, mass0, number_of_particles, bunchlength_rms, neps_x, neps_y,
+                        delta_rms, kind="bunched", circumference=None):
+    """Cut ``n_kicks`` equidistant space-charge kicks into the drifts of ``line`` and size
+    them from the line's own lattice functions -- the recipe the reference's PSB test
+    prepares (tests/test_madx_import.py:19-36: ``n_SCkicks = 120``, 1e11 protons,
+    ``bunchlength_rms = 1``, normalised emittances 1.5 um, ``delta_rms = 1e-3``), with
+    ``optics.twiss`` in place of the MAD-X twiss table:
+    ``sigma_x = sqrt(betx eps_x / (beta gamma) + (dx delta_rms)^2)`` at every kick, kick length
+    = circumference / n_kicks.  Returns the new Line."""
+    from . import optics
+
+    circ = line.get_length()
+    seg = circ / n_kicks
+    targets = [(k + 0.5) * seg for k in range(n_kicks)]
+    els, names = [], []
+    s, t = 0.0, 0
+    sc_ids = []
+    for el, nm in zip(line.elements, line.element_names):
+        if isinstance(el, (E.Drift, E.DriftExact)) and el.length > 0:
+            cls, rest, part = type(el), el.length, 0
+            while t < n_kicks and targets[t] <= s + rest:
+                head = targets[t] - s
+                if head > 0:
+                    els.append(cls(length=head))
+                    names.append("%s..%d" % (nm, part))
+                    part += 1
+                sc_ids.append(len(els))
+                els.append(None)
+                names.append("sc_%d" % t)
+                s, rest, t = targets[t], rest - head, t + 1
+            if rest > 0 or part == 0:
+                els.append(cls(length=rest))
+                names.append(nm if part == 0 else "%s..%d" % (nm, part))
+            s += rest
+        else:
+            els.append(el)
+            names.append(nm)
+    assert t == n_kicks, "could not place every space-charge kick inside a drift"
+    bare = Line([e if e is not None else E.Drift(length=0.0) for e in els], names)
+    tw = optics.twiss(bare)
+    bg = p0c / mass0
+    for i in sc_ids:
+        sx = float(np.sqrt(tw["betx"][i] * neps_x / bg + (tw["dx"][i] * delta_rms) ** 2))
+        sy = float(np.sqrt(tw["bety"][i] * neps_y / bg + (tw["dy"][i] * delta_rms) ** 2))
+        if kind == "bunched":
+            els[i] = E.SCQGaussProfile(number_of_particles=number_of_particles, bunchlength_rms=bunchlength_rms,
+                                       sigma_x=sx, sigma_y=sy, length=seg, x_co=0.0, y_co=0.0)
+        else:
+            els[i] = E.SCCoasting(number_of_particles=number_of_particles,
+                                  circumference=circumference or circ, sigma_x=sx, sigma_y=sy,
+                                  length=seg, x_co=0.0, y_co=0.0)
+    return Line(els, names)
+
+
+def matched_gaussian(line, n, rng, p0c, mass0, neps_x, neps_y, delta_rms, sigma_zeta):
+    """Gaussian beam matched to the lattice functions at the start of ``line``."""
+    from . import optics
+
+    tw = optics.twiss(line)
+    bg = p0c / mass0
+    delta = rng.normal(0, delta_rms, n)
+    cols = dict(zeta=rng.normal(0, sigma_zeta, n), delta=delta)
+    for u, pu, eps in (("x", "px", neps_x / bg), ("y", "py", neps_y / bg)):
+        beta, alpha = tw["bet" + u][0], tw["alf" + u][0]
+        g1, g2 = rng.normal(0, 1, n), rng.normal(0, 1, n)
+        cols[u] = np.sqrt(eps * beta) * g1 + tw["d" + u][0] * delta
+        cols[pu] = np.sqrt(eps / beta) * (g2 - alpha * g1) + tw["d" + pu][0] * delta
+    return cols
+
+
+def eta_sign(line, p0c, m0):
+    """Sign of the slip factor ``alfa_c - 1 / gamma0^2``."""
+    from . import optics
+
+    e0 = np.sqrt(p0c ** 2 + m0 ** 2)
+    return np.sign(optics.twiss(line)["alfa_c"] - (m0 / e0) ** 2)
+
+
+def config_psb(n=1_000_000, rank=0, n_sc=120, monitor_stores=0, monitor_ids=0, number_of_particles=1e11,
+               bunchlength_rms=1.0, rf_voltage=None, monitor_skip=1):
+    """C5: the PS Booster ring 1 of tests/psb/psb_fb_lhc.madx (flat-bottom optics,
+    PC = 0.571 GeV/c, QH = 4.22, QV = 4.45; 380 thin elements + 264 apertures from
+    psb_aperture.dbx), read by ``xline_b200.madx_input``, with 120 ``SCQGaussProfile`` kicks
+    (tests/test_madx_import.py:19-33) sized from ``optics.twiss``, an h = 1 RF voltage on the
+    first ``ACWFB`` cavity (the shipped strength file leaves it at 0; by default the voltage
+    that matches ``bunchlength_rms`` to ``delta_rms = 1e-3`` in the linear bucket, so that the
+    tracked bunch keeps the length the frozen space-charge profile assumes) and optionally one
+    BeamMonitor at the start of the ring.  Beam: Gaussian matched to the bare optics."""
+    line, meta = load_lattice("psb")
+    p0c, m0 = p0c_of(meta)
+    neps, delta_rms = 1.5e-6, 1e-3
+    line = install_spacecharge(line, n_sc, p0c, m0, number_of_particles, bunchlength_rms, neps, neps, delta_rms)
+    e0 = np.sqrt(p0c ** 2 + m0 ** 2)
+    frev = (p0c / e0) * 299792458.0 / line.get_length()
+    if rf_voltage is None:
+        from . import optics
+
+        beta0, gamma0 = p0c / e0, e0 / m0
+        eta = optics.twiss(line)["alfa_c"] - 1.0 / gamma0 ** 2
+        radius = line.get_length() / (2 * np.pi)
+        qs = abs(eta) * radius * delta_rms / bunchlength_rms       # sigma_z = |eta| R sigma_delta / Qs
+        rf_voltage = 2 * np.pi * beta0 ** 2 * e0 * qs ** 2 / abs(eta)   # Qs^2 = h |eta| V / (2 pi beta^2 E), h = 1
+    cav = [e for e in line.elements if isinstance(e, E.Cavity)][0]
+    # below transition (eta < 0): stable phase 0, xline lag in degrees (xline/elements.py:241)
+    cav.voltage, cav.frequency, cav.lag = float(rf_voltage), float(frev), 0.0 if eta_sign(line, p0c, m0) < 0 else 180.0
+    if monitor_stores > 0:
+        line.insert_element(0, E.BeamMonitor(num_stores=monitor_stores, start=0, skip=monitor_skip,
+                                             min_particle_id=0, max_particle_id=max(monitor_ids - 1, 0)), "monitor")
+    rng = np.random.default_rng(SEED0 + 1000 * 5 + rank)
+    cols = matched_gaussian(line, n, rng, p0c, m0, neps, neps, delta_rms, bunchlength_rms)
+    return line, cols, p0c, m0
+
+
 def config_petra4(n=1_000_000, rank=0, x_max=1.5e-3, y_max=0.8e-3):
     """C4: the PETRA IV lattice of examples/petra4/h7ba_n8.seq (4 886 placements; 2 rfcavity at
     500 MHz), read by ``xline_b200.madx_input`` and made thin with 4 TEAPOT slices per

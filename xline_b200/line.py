@@ -231,7 +231,7 @@ class Line(E.Element):
             cur = list(getattr(element, attr))
             cur += [0] * (len(extra) - len(cur))
             for i, c in enumerate(extra):
-                cur[i] += c
+                cur[i] = float(cur[i] + c)
             setattr(element, attr, cur)
         self.invalidate()
 
@@ -396,7 +396,7 @@ class Line(E.Element):
     # ------------------------------------------------------------------ loaders
     @classmethod
     def from_madx_sequence(cls, sequence, classes=None, ignored_madtypes=(), exact_drift=False,
-                           drift_threshold=1e-6, install_apertures=False):
+                           drift_threshold=1e-6, install_apertures=False, apply_madx_errors=False):
         """xline/line.py:297-324 for a thin ``madx_input.MadSequence`` (or any object with
         ``elements`` / ``element_positions()`` / ``length`` like a cpymad sequence)."""
         from .madx_input import iter_from_madx_sequence
@@ -406,7 +406,36 @@ class Line(E.Element):
                                               exact_drift, drift_threshold, install_apertures):
             names.append(nm)
             els.append(el)
-        return cls(els, names)
+        line = cls(els, names)
+        if apply_madx_errors:
+            line._apply_madx_errors(sequence)
+        return line
+
+    def _apply_madx_errors(self, madx_sequence):
+        """xline/line.py:417-489: turn the alignment / field errors attached to the elements of
+        the expanded MAD-X sequence into XYShift / SRotation wrappers and multipole
+        coefficients.  Returns the names of elements that carry errors but are not in this line."""
+        not_found = []
+        for element, name in zip(madx_sequence.expanded_elements, madx_sequence.expanded_element_names()):
+            if name not in self.element_names:
+                if element.align_errors or element.field_errors:
+                    not_found.append(name)
+                    continue
+            if element.align_errors:
+                err = element.align_errors
+                if err.dx or err.dy:
+                    self._add_offset_error_to(name, err.dx, err.dy)
+                if err.dpsi:
+                    self._add_tilt_error_to(name, angle=err.dpsi / deg2rad)
+                if err.arex or err.arey:
+                    self._add_aperture_offset_error_to(name, err.arex, err.arey)
+            if element.field_errors:
+                dkn, dks = np.asarray(element.field_errors.dkn), np.asarray(element.field_errors.dks)
+                if dkn.any() or dks.any():
+                    last = max(np.flatnonzero(dkn)[-1] if dkn.any() else 0,
+                               np.flatnonzero(dks)[-1] if dks.any() else 0) + 1
+                    self._add_multipole_error_to(name, dkn[:last], dks[:last])
+        return not_found
 
     @classmethod
     def from_sixinput(cls, sixinput, classes=None):
