@@ -11,7 +11,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
 turns = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 which = sys.argv[3] if len(sys.argv) > 3 else "c3"
 line, cols, p0c, m0 = {"c3": configs.config_lhc_beambeam, "c4": configs.config_petra_like,
-                       "c5": configs.config_psb_like, "c4r": configs.config_petra4}[which](n)
+                       "c5": configs.config_psb, "c5like": configs.config_psb_like,
+                       "c4r": configs.config_petra4}[which](n)
 ops = line.algorithmic_ops_per_turn()
 fl, _ = _cabi.measure_fp64_peak(3)
 print("elements", len(line), "alg ops/turn", ops, "records", line.pack().record_counts)

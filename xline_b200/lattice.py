@@ -79,24 +79,39 @@ def _pad(seq, size):
     return a
 
 
-def _gauss_field_block(rec, sigma_x, sigma_y, min_sigma_diff):
-    """Three pairs describing a frozen 2-D Gaussian of fixed sigmas
-    (be_beamfields/gaussian_fields.py:107-121, 5-21, 29-99)."""
+FIELD_BLOCK_PAIRS = {True: 3, False: 6}  # strict / fast encoding
+
+
+def _gauss_field_block(rec, sigma_x, sigma_y, min_sigma_diff, strict):
+    """The pairs describing a frozen 2-D Gaussian of fixed sigmas
+    (be_beamfields/gaussian_fields.py:107-121, 5-21, 29-99): ``[sx, sy][kind, 0][A, 0]`` and,
+    in the fast encoding, three more pairs with everything Bassetti-Erskine needs that depends
+    on the sigmas only -- ``[1/S, A sqrt(pi)/S][small/big, big/small][1/(2 big^2), 1/(2 small^2)]``
+    -- so that the kernel spends no square root and no division on them per particle."""
     inv2pieps0 = 1.0 / (2.0 * math.pi * epsilon_0)
     if abs(sigma_x - sigma_y) < min_sigma_diff:
         rec.f(sigma_x, sigma_y).i(0, 0).f(inv2pieps0, 0.0)
+        if not strict:
+            rec.f(0.0, 0.0).f(0.0, 0.0).f(0.0, 0.0)
         return
     if sigma_x == sigma_y:
         # gaussian_fields.py:91-92 -> 1.0/0.0 (tests/test_beamfields.py:86-98)
         raise ZeroDivisionError("float division by zero")
     rec.f(sigma_x, sigma_y).i(1 if sigma_x > sigma_y else 2, 0).f(inv2pieps0, 0.0)
+    if not strict:
+        big, small = max(sigma_x, sigma_y), min(sigma_x, sigma_y)
+        S = math.sqrt(2.0 * (big * big - small * small))
+        inv_s = 1.0 / S
+        rec.f(inv_s, inv2pieps0 * 1.772453850905516 * inv_s)
+        rec.f(small / big, big / small)
+        rec.f(1.0 / (2.0 * big * big), 1.0 / (2.0 * small * small))
 
 
-def _pack_beambeam4d(el, idx):
+def _pack_beambeam4d(el, idx, strict):
     """be_beamfields/beambeam.py:45-82: min_sigma_diff hard-coded to 1e-10 (:63)."""
     rec = _Rec(T_BEAMBEAM4D, 0, idx)
     rec.f(el.x_bb, el.y_bb)
-    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), 1e-10)
+    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), 1e-10, strict)
     rec.f(el.d_px, el.d_py)
     rec.f(el.beta_r, float(el.charge) * qe)
     return rec
@@ -117,7 +132,7 @@ def _qgauss_cq(q, eps=1e-6):
     return cq
 
 
-def _pack_spacecharge(el, idx):
+def _pack_spacecharge(el, idx, strict):
     """be_beamfields/spacecharge.py:26-52, 80-104, 137-177."""
     name = type(el).__name__
     if name == "SCCoasting":
@@ -128,7 +143,7 @@ def _pack_spacecharge(el, idx):
         kind = {0: 2, 1: 3}.get(int(el.method), 0)
     rec = _Rec(T_SPACECHARGE, kind, idx)
     rec.f(el.x_co, el.y_co)
-    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), float(el.min_sigma_diff))
+    _gauss_field_block(rec, float(el.sigma_x), float(el.sigma_y), float(el.min_sigma_diff), strict)
     base = float(el.number_of_particles) * qe * float(el.length)
     if name == "SCCoasting":
         rec.f(base / float(el.circumference), 0.0)
@@ -302,9 +317,9 @@ def _pack_element(el, idx, strict, monitors):
         rec.i(el.max_particle_id, 1 if el.is_rolling else 0).i(off, 0)
         return rec
     if name == "BeamBeam4D":
-        return _pack_beambeam4d(el, idx)
+        return _pack_beambeam4d(el, idx, strict)
     if name in ("SCCoasting", "SCQGaussProfile", "SCInterpolatedProfile"):
-        return _pack_spacecharge(el, idx)
+        return _pack_spacecharge(el, idx, strict)
     if name == "BeamBeam6D":
         return _pack_beambeam6d(el, idx)
     if name == "LimitPolygon":
