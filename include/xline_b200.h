@@ -124,6 +124,8 @@ typedef struct xlb_lattice {
 #define XLB_F_STRICT 1u      /* lattice encoded for / kernel evaluates in the reference's
                                 operation order without FMA contraction                 */
 #define XLB_F_BEAMFIELDS 2u  /* lattice contains BEAMBEAM4D/6D or SPACECHARGE records    */
+#define XLB_F_BB6D 4u        /* lattice contains BEAMBEAM6D records (implies BEAMFIELDS):
+                                selects the kernels that carry the 6D lens            */
 
 /* Particle set, mirrors the attributes the reference's elements read and write
  * (SURVEY.md §8a row a2).  All arrays have length n.  chi and charge_ratio may be NULL

@@ -24,8 +24,9 @@ UNITS = [
     ("cabi", "cabi.cu", []),
     ("track_fast", "track_fast.cu", []),
     ("track_strict", "track_strict.cu", ["-fmad=false"]),
-    ("track_fast_bf", "track_fast.cu", ["-DXLB_BEAMFIELDS=1"]),
-    ("track_strict_bf", "track_strict.cu", ["-DXLB_BEAMFIELDS=1", "-fmad=false"]),
+    ("track_fast_bf", "track_fast.cu", ["-DXLB_BEAMFIELDS=1"]),        # + BeamBeam4D, space charge
+    ("track_fast_bf6", "track_fast.cu", ["-DXLB_BEAMFIELDS=2"]),       # + BeamBeam6D
+    ("track_strict_bf", "track_strict.cu", ["-DXLB_BEAMFIELDS=2", "-fmad=false"]),
 ]
 HEADERS = ["track_impl.cuh", "kargs.h", "variants.inc", "beamfields.cuh", "faddeeva.cuh",
            os.path.join("..", "..", "include", "xline_b200.h")]

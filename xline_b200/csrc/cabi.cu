@@ -16,6 +16,7 @@
 
 namespace xlb {
 const Variant *fast_bf_variants(int *n);
+const Variant *fast_bf6_variants(int *n);
 const Variant *strict_bf_variants(int *n);
 
 static thread_local std::string g_err;
@@ -219,13 +220,14 @@ static int compact_alive(const long long *state, long long n, int *idx_out, int 
 // ------------------------------------------------------------------ variant selection
 // Among the variants of the requested particles-per-thread, the one with the smallest
 // launch-bounds ceiling that still admits `threads` (tighter ceilings allow more registers).
-static const Variant *pick_variant(bool strict, bool beamfields, int ppt, int threads, bool trace) {
+static const Variant *pick_variant(bool strict, bool beamfields, bool bb6d, int ppt, int threads,
+                                   bool trace) {
   int n = 0;
   const Variant *tab;
   if (strict)
     tab = beamfields ? strict_bf_variants(&n) : strict_variants(&n);
   else
-    tab = beamfields ? fast_bf_variants(&n) : fast_variants(&n);
+    tab = beamfields ? (bb6d ? fast_bf6_variants(&n) : fast_bf_variants(&n)) : fast_variants(&n);
   const Variant *best = nullptr;
   for (int i = 0; i < n; ++i) {
     const Variant &v = tab[i];
@@ -284,6 +286,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
 
   const bool strict = (lat->flags & XLB_F_STRICT) != 0;
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
+  const bool bb6d = (lat->flags & XLB_F_BB6D) != 0;
   // defaults from the B200 sweep (scripts/probe_bench_sweep.py): thin-lens lattices run best
   // with 3 particles per thread in 128-thread CTAs (3 CTAs/SM, 164 registers, no spills)
   const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread
@@ -292,7 +295,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const bool trace = o->trace != nullptr;
   if (trace && (o->num_turns != 1 || o->trace_particles < 1))
     return fail(XLB_EINVAL, "element-by-element trace needs num_turns == 1 and trace_particles >= 1");
-  const Variant *v = pick_variant(strict, beamfields, ppt_req, threads_req, trace);
+  const Variant *v = pick_variant(strict, beamfields, bb6d, ppt_req, threads_req, trace);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
   int threads = trace ? v->threads
                       : (o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req));
@@ -529,6 +532,8 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
         case XLB_T_BEAMBEAM6D:
           if (!(lat->flags & XLB_F_BEAMFIELDS))
             return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
+          if (tag == XLB_T_BEAMBEAM6D && !(lat->flags & XLB_F_BB6D))
+            return fail(XLB_ELATTICE, "BeamBeam6D record without XLB_F_BB6D");
           if (pairs < 6) return fail(XLB_ELATTICE, "bad beam-field record length");
           break;
         default: {
@@ -737,19 +742,20 @@ int xlb_measure_dfma_latency(double *cycles_per_dfma, int n) {
 }
 
 int xlb_kernel_variant_count(void) {
-  int a = 0, b = 0, c = 0, d = 0;
+  int a = 0, b = 0, c = 0, d = 0, e = 0;
   fast_variants(&a);
   strict_variants(&b);
   fast_bf_variants(&c);
   strict_bf_variants(&d);
-  return a + b + c + d;
+  fast_bf6_variants(&e);
+  return a + b + c + d + e;
 }
 
 int xlb_kernel_variant_info(int i, char *name, int name_len, int *regs, int *max_threads) {
-  int n[4];
-  const Variant *t[4] = {fast_variants(&n[0]), strict_variants(&n[1]), fast_bf_variants(&n[2]),
-                         strict_bf_variants(&n[3])};
-  for (int k = 0; k < 4; ++k) {
+  int n[5];
+  const Variant *t[5] = {fast_variants(&n[0]), strict_variants(&n[1]), fast_bf_variants(&n[2]),
+                         strict_bf_variants(&n[3]), fast_bf6_variants(&n[4])};
+  for (int k = 0; k < 5; ++k) {
     if (i < n[k]) {
       const Variant &v = t[k][i];
       if (name && name_len > 0) {

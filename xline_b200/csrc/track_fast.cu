@@ -3,7 +3,13 @@
 #ifndef XLB_BEAMFIELDS
 #define XLB_BEAMFIELDS 0
 #endif
-#if XLB_BEAMFIELDS
+// XLB_BEAMFIELDS: 0 = thin lenses only, 1 = + BeamBeam4D and space charge, 2 = + BeamBeam6D.
+// The 6D lens is compiled into its own set of kernels: its register appetite makes ptxas
+// spill in the dispatch loop of every kernel that contains it, whether or not a lattice has
+// such a lens (ncu on the PS Booster: 6 % of all executed instructions were LDL/STL).
+#if XLB_BEAMFIELDS == 2
+#define XLB_NS fast_bf6
+#elif XLB_BEAMFIELDS
 #define XLB_NS fast_bf
 #else
 #define XLB_NS fast_lean
@@ -21,13 +27,20 @@ XLB_DEF_TRACE_VARIANT()
 XLB_DEF_VARIANT(1, 256, 2)
 XLB_DEF_VARIANT(2, 256, 2)
 XLB_DEF_VARIANT(3, 128, 3)
+#if XLB_BEAMFIELDS == 2
+#define XLB_BF_SUFFIX "/beamfields6d"
+#define XLB_BF_TABLE_FN fast_bf6_variants
+#else
+#define XLB_BF_SUFFIX "/beamfields"
+#define XLB_BF_TABLE_FN fast_bf_variants
+#endif
 static const Variant fast_bf_table[] = {
-    XLB_VARIANT_ENTRY("fast/ppt1/t256/beamfields", 1, 256, 2),
-    XLB_VARIANT_ENTRY("fast/ppt2/t256/beamfields", 2, 256, 2),
-    XLB_VARIANT_ENTRY("fast/ppt3/t128/beamfields", 3, 128, 3),
-    XLB_TRACE_ENTRY("fast/trace"),
+    XLB_VARIANT_ENTRY("fast/ppt1/t256" XLB_BF_SUFFIX, 1, 256, 2),
+    XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_BF_SUFFIX, 2, 256, 2),
+    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_BF_SUFFIX, 3, 128, 3),
+    XLB_TRACE_ENTRY("fast/trace" XLB_BF_SUFFIX),
 };
-const Variant *fast_bf_variants(int *n) {
+const Variant *XLB_BF_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(fast_bf_table) / sizeof(fast_bf_table[0]));
   return fast_bf_table;
 }

@@ -29,6 +29,7 @@ T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D = 16, 17, 18
 
 F_STRICT = 1
 F_BEAMFIELDS = 2
+F_BB6D = 4
 
 DEFAULT_CHUNK_WORDS = 2048  # 16 KiB per TMA bulk copy, 3 in flight per CTA
 MONITOR_FIELDS = ("x", "px", "y", "py", "zeta", "delta", "at_turn")
@@ -541,6 +542,8 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
         tag = rec.tag
         if tag in (T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D):
             flags |= F_BEAMFIELDS
+            if tag == T_BEAMBEAM6D:
+                flags |= F_BB6D
         counts[tag] = counts.get(tag, 0) + 1
         recs.append(rec.words())
     biggest = max([len(r) for r in recs] + [0])

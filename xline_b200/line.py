@@ -316,13 +316,14 @@ class Line(E.Element):
             if particles_per_thread == 0 and (packed.flags & 2) and not strict:
                 # beam-field lattice: the thin-lens records still dominate when lenses are
                 # sparse (LHC + 74 lenses: 3 particles/thread wins); dense space-charge
-                # lattices run best with one particle per thread (no spilling in the field
-                # code, whose paired Faddeeva evaluation already carries two independent chains;
-                # PS Booster with 120 kicks/turn: 1.37e8 vs 1.13e8 vs 1.09e8 for 1 / 2 / 3)
+                # lattices prefer fewer (PS Booster with 120 kicks/turn: 1.57e8 / 1.69e8 / 1.26e8
+                # particle-turns/s for 1 / 2 / 3; the kernels that carry the 6D lens spill and
+                # are best with 1)
                 nbf = sum(v for k, v in packed.record_counts.items() if k in (16, 17, 18))
                 sparse = nbf < 0.05 * max(sum(packed.record_counts.values()), 1)
+                dense_ppt = 1 if packed.record_counts.get(18, 0) else 2
                 particles_per_thread, threads_per_block = ((3, threads_per_block or 128) if sparse
-                                                           else (1, threads_per_block or 256))
+                                                           else (dense_ppt, threads_per_block or 256))
             opts = _cabi.TrackOptions()
             opts.num_turns = int(num_turns)
             opts.particles_per_thread = int(particles_per_thread)
