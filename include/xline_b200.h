@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XLB_ABI_VERSION 1
+#define XLB_ABI_VERSION 2
 
 /* error codes */
 #define XLB_OK 0
@@ -119,13 +119,26 @@ typedef struct xlb_lattice {
   int32_t n_chunks;
   int32_t n_elements;    /* length of the reference Line (size of loss tallies)         */
   uint32_t flags;        /* XLB_F_* below                                               */
+  /* Segmented lattice (fast encoding of lattices with BeamBeam6D lenses): the chunks form
+     n_segments consecutive groups, each terminated by END_TURN, that are executed one after
+     the other every turn -- XLB_SEG_MAIN groups by the tracking kernel, XLB_SEG_BB6D groups
+     (one chunk holding one BEAMBEAM6D record) by the stand-alone 6D-lens kernel.  The last
+     group is a MAIN group (possibly empty); it is the one that counts the turn.  `segments`
+     is a HOST array of n_segments triples {first_chunk, n_chunks, kind}, also when `words`
+     is device memory.  n_segments == 0: the whole lattice is one MAIN group.            */
+  int32_t n_segments;
+  const int32_t *segments;
 } xlb_lattice_t;
+
+#define XLB_SEG_MAIN 0
+#define XLB_SEG_BB6D 1
 
 #define XLB_F_STRICT 1u      /* lattice encoded for / kernel evaluates in the reference's
                                 operation order without FMA contraction                 */
-#define XLB_F_BEAMFIELDS 2u  /* lattice contains BEAMBEAM4D/6D or SPACECHARGE records    */
-#define XLB_F_BB6D 4u        /* lattice contains BEAMBEAM6D records (implies BEAMFIELDS):
-                                selects the kernels that carry the 6D lens            */
+#define XLB_F_BEAMFIELDS 2u  /* the MAIN groups contain BEAMBEAM4D/6D or SPACECHARGE records */
+#define XLB_F_BB6D 4u        /* lattice contains BEAMBEAM6D records: in MAIN groups (then
+                                BEAMFIELDS is set too and the kernels that carry the 6D
+                                lens are used) or in XLB_SEG_BB6D groups                */
 
 /* Particle set, mirrors the attributes the reference's elements read and write
  * (SURVEY.md §8a row a2).  All arrays have length n.  chi and charge_ratio may be NULL

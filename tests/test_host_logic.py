@@ -189,7 +189,7 @@ def test_cabi_exports_every_declared_symbol():
     L = _cabi.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.xlb_abi_version() == 1
+    assert L.xlb_abi_version() == _cabi.ABI_VERSION == 2
     # argument validation happens before any CUDA call
     assert L.xlb_track_device(None, None, None, None) == -1
     assert b"null" in L.xlb_last_error()
@@ -355,3 +355,62 @@ def test_line_like_reference_test_line():
     merged = xl.Line([xl.Multipole(knl=[0, 1.0]), xl.Multipole(knl=[1e-3, 0.5, 2.0], ksl=[0, 0.1])]).merge_consecutive_multipoles()
     assert len(merged) == 1 and merged.elements[0].knl == [1e-3, 1.5, 2.0] and merged.elements[0].ksl == [0, 0.1, 0]
     assert line2.get_element_ids_of_type(xl.Drift, start_idx_offset=2) == [2, 4]
+
+
+def _bb6d(**kw):
+    base = dict(phi=1e-4, alpha=0.3, x_bb_co=1e-5, y_bb_co=-2e-5, charge_slices=[1e10, 2e10, 1e10],
+                zeta_slices=[0.05, 0.0, -0.05], sigma_11=1e-9, sigma_12=1e-12, sigma_13=0.0, sigma_14=0.0,
+                sigma_22=1e-11, sigma_23=0.0, sigma_24=0.0, sigma_33=2e-9, sigma_34=-1e-12, sigma_44=3e-11)
+    base.update(kw)
+    return xl.BeamBeam6D(**base)
+
+
+def test_pack_segments_lattices_with_6d_lenses(tmp_path):
+    """Fast encoding: every BeamBeam6D record sits alone in a chunk of its own, the lattice is
+    a sequence of segments (xlb_lattice_t::segments) and the closing segment is a tracking
+    segment; strict / element-by-element encodings stay one piece."""
+    els = [xl.Drift(1.0), xl.Multipole(knl=[0, 0.1]), _bb6d(), xl.LimitRect(min_x=-1, max_x=1, min_y=-1, max_y=1),
+           xl.Drift(2.0), _bb6d(phi=2e-4), _bb6d(phi=3e-4), xl.BeamBeam4D(charge=1e10, sigma_x=1e-4, sigma_y=2e-4),
+           xl.Drift(1.0), _bb6d(phi=4e-4)]
+    line = xl.Line(els)
+    pk = line.pack()
+    S, M, B = pk.segments.tolist(), lattice.SEG_MAIN, lattice.SEG_BB6D
+    assert [s[2] for s in S] == [M, B, M, B, B, M, B, M]
+    assert [s[0] for s in S] == list(range(8)) and all(s[1] == 1 for s in S) and pk.n_chunks == 8
+    assert pk.flags & lattice.F_BB6D and pk.flags & lattice.F_BEAMFIELDS       # the BeamBeam4D
+    assert not (xl.Line(els[:7]).pack().flags & lattice.F_BEAMFIELDS)          # 6D lenses only: lean kernels
+    for first, _, kind in S:
+        hdr = int(pk.words[first * pk.chunk_words])
+        assert ((hdr & 0xff) == lattice.T_BEAMBEAM6D) == (kind == B)
+    # element indices stay those of the Line
+    lens_idx = [int(pk.words[s[0] * pk.chunk_words]) >> 32 for s in S if s[2] == B]
+    assert lens_idx == [2, 5, 6, 9]
+    assert line.pack(strict=True).segments is None and (line.pack(strict=True).flags & lattice.F_BEAMFIELDS)
+    line.split_lenses = False
+    whole = line.pack()
+    assert whole.segments is None and whole.n_chunks == 1 and whole.flags & lattice.F_BEAMFIELDS
+    line.split_lenses = True
+    # on-disk round trip keeps the segment table
+    fn = str(tmp_path / "seg.npz")
+    pk.save(fn)
+    back = lattice.PackedLattice.load(fn)
+    assert np.array_equal(back.segments, pk.segments) and back.segments.dtype == np.int32
+    L = _cabi.lib()
+    lat = back.c_lattice()
+    assert L.xlb_lattice_validate(C.byref(lat)) == 0
+    # the validator knows the rules
+    seg = pk.segments.copy()
+    seg[1, 2] = M                                   # a 6D record inside a tracking segment
+    lat = pk.c_lattice()
+    lat.segments = seg.ctypes.data
+    assert L.xlb_lattice_validate(C.byref(lat)) != 0 and b"MAIN segment" in L.xlb_last_error()
+    seg = pk.segments.copy()
+    seg[2, 0] = 3                                   # hole in the tiling
+    lat.segments = seg.ctypes.data
+    assert L.xlb_lattice_validate(C.byref(lat)) != 0 and b"tile" in L.xlb_last_error()
+    seg = pk.segments[:-1].copy()                   # must end with a tracking segment / cover all chunks
+    lat.segments, lat.n_segments = seg.ctypes.data, len(seg)
+    assert L.xlb_lattice_validate(C.byref(lat)) != 0
+    lat = pk.c_lattice()
+    lat.flags = pk.flags & ~lattice.F_BB6D
+    assert L.xlb_lattice_validate(C.byref(lat)) != 0 and b"XLB_F_BB6D" in L.xlb_last_error()

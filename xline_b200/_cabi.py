@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxline_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "xlb_abi_version", "xlb_last_error", "xlb_lattice_validate", "xlb_track_device",
@@ -23,6 +23,7 @@ class Lattice(C.Structure):
     _fields_ = [
         ("words", C.c_void_p), ("n_words", C.c_int64), ("chunk_words", C.c_int32),
         ("n_chunks", C.c_int32), ("n_elements", C.c_int32), ("flags", C.c_uint32),
+        ("n_segments", C.c_int32), ("segments", C.c_void_p),
     ]
 
 

@@ -258,6 +258,22 @@ static int check_lattice_header(const xlb_lattice_t *lat) {
     return fail(XLB_ELATTICE, "n_words != chunk_words * n_chunks");
   if (reinterpret_cast<uintptr_t>(lat->words) & 15)
     return fail(XLB_ELATTICE, "lattice words must be 16-byte aligned");
+  if (lat->n_segments < 0 || (lat->n_segments > 0 && !lat->segments))
+    return fail(XLB_ELATTICE, "bad segment table");
+  int next = 0;
+  for (int k = 0; k < lat->n_segments; ++k) {
+    const int32_t *sg = lat->segments + 3 * k;
+    if (sg[0] != next || sg[1] < 1) return fail(XLB_ELATTICE, "segments must tile the chunks in order");
+    if (sg[2] != XLB_SEG_MAIN && sg[2] != XLB_SEG_BB6D) return fail(XLB_ELATTICE, "unknown segment kind");
+    if (sg[2] == XLB_SEG_BB6D && (sg[1] != 1 || !(lat->flags & XLB_F_BB6D) || (lat->flags & XLB_F_STRICT)))
+      return fail(XLB_ELATTICE, "a 6D-lens segment is one chunk of a fast lattice flagged XLB_F_BB6D");
+    next += sg[1];
+  }
+  if (lat->n_segments > 0) {
+    if (next != lat->n_chunks) return fail(XLB_ELATTICE, "segments do not cover all chunks");
+    if (lat->segments[3 * (lat->n_segments - 1) + 2] != XLB_SEG_MAIN)
+      return fail(XLB_ELATTICE, "the last segment must be a MAIN segment");
+  }
   return XLB_OK;
 }
 
@@ -286,7 +302,8 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
 
   const bool strict = (lat->flags & XLB_F_STRICT) != 0;
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
-  const bool bb6d = (lat->flags & XLB_F_BB6D) != 0;
+  const bool split = lat->n_segments > 1;  // 6D lenses run as kernels of their own
+  const bool bb6d = (lat->flags & XLB_F_BB6D) != 0 && !split;
   // defaults from the B200 sweep (scripts/probe_bench_sweep.py): thin-lens lattices run best
   // with 3 particles per thread in 128-thread CTAs (3 CTAs/SM, 164 registers, no spills)
   const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread
@@ -295,6 +312,8 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const bool trace = o->trace != nullptr;
   if (trace && (o->num_turns != 1 || o->trace_particles < 1))
     return fail(XLB_EINVAL, "element-by-element trace needs num_turns == 1 and trace_particles >= 1");
+  if (split && (trace || strict))
+    return fail(XLB_EINVAL, "segmented lattices are for the fast kernels without trace");
   const Variant *v = pick_variant(strict, beamfields, bb6d, ppt_req, threads_req, trace);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
   int threads = trace ? v->threads
@@ -377,6 +396,34 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     a.n_blocks = static_cast<unsigned int>(blocks);
     a.n_items = static_cast<unsigned int>(blocks);
     a.turns_per_item = turns;
+    a.count_turns = 1;
+    if (split) {
+      // turn by turn, segment by segment: tracking kernel up to the next 6D lens, the lens
+      // kernel, and so on; the closing MAIN segment counts the turn
+      a.num_turns = 1;
+      a.turns_per_item = 1;
+      const int lens_threads = 128;
+      const int lens_blocks = static_cast<int>((n_active + lens_threads - 1) / lens_threads);
+      for (int t = 0; t < turns; ++t) {
+        for (int k = 0; k < lat->n_segments; ++k) {
+          const int32_t *sg = lat->segments + 3 * k;
+          const uint64_t *first = lat->words + static_cast<size_t>(sg[0]) * lat->chunk_words;
+          if (sg[2] == XLB_SEG_BB6D) {
+            fast_bb6d_launch(a, reinterpret_cast<const unsigned long long *>(first), lens_blocks,
+                             lens_threads, st);
+          } else {
+            a.lat = first;
+            a.n_chunks = sg[1];
+            a.count_turns = (k == lat->n_segments - 1) ? 1 : 0;
+            v->launch(a, blocks, threads, smem, st);
+          }
+          g_stats.kernel_launches += 1;
+        }
+      }
+      XLB_CUDA(cudaGetLastError());
+      g_stats.blocks = blocks;
+      g_stats.threads = threads;
+    } else {
     if (tpi > 0 && turns > tpi && blocks > resident) {
       // persistent CTAs + device-side work queue: (block, turn segment) items, segment-major
       const long long segs = (turns + tpi - 1) / tpi;
@@ -394,6 +441,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     g_stats.kernel_launches += 1;
     g_stats.blocks = blocks;
     g_stats.threads = threads;
+    }
     done += turns;
     if (done >= o->num_turns) break;
     // survivors: read the loss counter; re-compact when enough lanes went idle
@@ -493,6 +541,15 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
   int rc = check_lattice_header(lat);
   if (rc != XLB_OK) return rc;
   bool saw_end_turn = false;
+  // last chunk of every segment (of the lattice when it is not segmented) and the chunks
+  // that belong to 6D-lens segments
+  std::vector<char> seg_last(lat->n_chunks, 0), lens_chunk(lat->n_chunks, 0);
+  seg_last[lat->n_chunks - 1] = 1;
+  for (int k = 0; k < lat->n_segments; ++k) {
+    const int32_t *sg = lat->segments + 3 * k;
+    seg_last[sg[0] + sg[1] - 1] = 1;
+    if (sg[2] == XLB_SEG_BB6D) lens_chunk[sg[0]] = 1;
+  }
   for (int c = 0; c < lat->n_chunks; ++c) {
     const uint64_t *w = lat->words + static_cast<size_t>(c) * lat->chunk_words;
     int pos = 0;
@@ -505,12 +562,12 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
       int want = -1;  // expected record length in pairs, -1 = variable
       switch (tag) {
         case XLB_T_END_TURN:
-          if (c != lat->n_chunks - 1) return fail(XLB_ELATTICE, "END_TURN before the last chunk");
+          if (!seg_last[c]) return fail(XLB_ELATTICE, "END_TURN before the last chunk");
           saw_end_turn = true;
           closed = true;
           break;
         case XLB_T_END_CHUNK:
-          if (c == lat->n_chunks - 1) return fail(XLB_ELATTICE, "last chunk must end with END_TURN");
+          if (seg_last[c]) return fail(XLB_ELATTICE, "last chunk must end with END_TURN");
           closed = true;
           break;
         case XLB_T_DRIFT:
@@ -530,8 +587,15 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
         case XLB_T_BEAMBEAM4D:
         case XLB_T_SPACECHARGE:
         case XLB_T_BEAMBEAM6D:
-          if (!(lat->flags & XLB_F_BEAMFIELDS))
-            return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
+          if (lens_chunk[c]) {
+            if (tag != XLB_T_BEAMBEAM6D || pos != 0)
+              return fail(XLB_ELATTICE, "a 6D-lens segment holds exactly one BEAMBEAM6D record");
+          } else {
+            if (!(lat->flags & XLB_F_BEAMFIELDS))
+              return fail(XLB_ELATTICE, "beam-field record without XLB_F_BEAMFIELDS");
+            if (tag == XLB_T_BEAMBEAM6D && lat->n_segments > 1)
+              return fail(XLB_ELATTICE, "BEAMBEAM6D record in a MAIN segment of a segmented lattice");
+          }
           if (tag == XLB_T_BEAMBEAM6D && !(lat->flags & XLB_F_BB6D))
             return fail(XLB_ELATTICE, "BeamBeam6D record without XLB_F_BB6D");
           if (pairs < 6) return fail(XLB_ELATTICE, "bad beam-field record length");
@@ -557,6 +621,8 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           return fail(XLB_ELATTICE, buf);
         }
       }
+      if (lens_chunk[c] && tag != XLB_T_BEAMBEAM6D && tag != XLB_T_END_TURN)
+        return fail(XLB_ELATTICE, "a 6D-lens segment holds exactly one BEAMBEAM6D record");
       if (!closed && (pairs < 1 || (want >= 0 && pairs != want))) {
         char buf[112];
         snprintf(buf, sizeof buf, "record of tag %d in chunk %d at word %d has size %d, expected %d",

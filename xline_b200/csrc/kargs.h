@@ -29,6 +29,9 @@ struct KArgs {
   unsigned int *queue;
   unsigned int n_blocks, n_items;
   int turns_per_item;
+  // added to the per-particle turn counter at every END_TURN: 1, except for the passes over
+  // the leading segments of a segmented lattice (xlb_lattice_t::segments), where it is 0
+  int count_turns;
   // element-by-element trace (debug kernels only): [n_elements][6][trace_n] fp64
   double *trace;
   long long trace_n;
@@ -40,6 +43,10 @@ struct Variant {
   const void *func;
   void (*launch)(const KArgs &, int blocks, int threads, size_t smem, void *stream);
 };
+
+// The 6D beam-beam lens as a kernel of its own (segmented lattices): one particle per thread,
+// `rec` = the BEAMBEAM6D record in the device copy of the lattice.
+void fast_bb6d_launch(const KArgs &a, const unsigned long long *rec, int blocks, int threads, void *stream);
 
 const Variant *fast_variants(int *n);
 const Variant *strict_variants(int *n);

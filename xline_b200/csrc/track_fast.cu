@@ -44,6 +44,12 @@ const Variant *XLB_BF_TABLE_FN(int *n) {
   *n = static_cast<int>(sizeof(fast_bf_table) / sizeof(fast_bf_table[0]));
   return fast_bf_table;
 }
+#if XLB_BEAMFIELDS == 2
+void fast_bb6d_launch(const KArgs &a, const unsigned long long *rec, int blocks, int threads, void *stream) {
+  bf::bb6d_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, reinterpret_cast<const double2 *>(rec));
+}
+#endif
 #else
 XLB_DEF_VARIANT(1, 128, 5)
 XLB_DEF_VARIANT(1, 256, 3)

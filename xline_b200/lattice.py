@@ -331,7 +331,9 @@ def _pack_element(el, idx, strict, monitors):
 class PackedLattice:
     """Result of :func:`pack_line`: ``words`` (uint64 numpy array, chunked) + metadata."""
 
-    def __init__(self, words, chunk_words, n_chunks, n_elements, flags, monitors, counts):
+    def __init__(self, words, chunk_words, n_chunks, n_elements, flags, monitors, counts, segments=None):
+        # int32 [n_segments, 3] = first_chunk, n_chunks, kind (xlb_lattice_t::segments) or None
+        self.segments = None if segments is None else np.ascontiguousarray(segments, dtype=np.int32)
         self.words = words
         self.chunk_words = chunk_words
         self.n_chunks = n_chunks
@@ -354,7 +356,8 @@ class PackedLattice:
             monitor_layout=np.array([[m["element_index"], m["offset"], m["num_stores"], m["nn"]]
                                      for m in self.monitor_layout], dtype=np.int64).reshape(-1, 4),
             record_tags=np.array(sorted(self.record_counts), dtype=np.int64),
-            record_counts=np.array([self.record_counts[k] for k in sorted(self.record_counts)], dtype=np.int64))
+            record_counts=np.array([self.record_counts[k] for k in sorted(self.record_counts)], dtype=np.int64),
+            segments=(np.zeros((0, 3), dtype=np.int32) if self.segments is None else self.segments))
 
     @classmethod
     def load(cls, path):
@@ -363,7 +366,20 @@ class PackedLattice:
                   for r in d["monitor_layout"]]
         counts = {int(k): int(v) for k, v in zip(d["record_tags"], d["record_counts"])}
         return cls(np.ascontiguousarray(d["words"], dtype=np.uint64), int(d["chunk_words"]), int(d["n_chunks"]),
-                   int(d["n_elements"]), int(d["flags"]), dict(layout=layout, words=int(d["monitor_words"])), counts)
+                   int(d["n_elements"]), int(d["flags"]), dict(layout=layout, words=int(d["monitor_words"])), counts,
+                   d["segments"] if "segments" in d and len(d["segments"]) else None)
+
+    def c_lattice(self, words_ptr=None):
+        """The ``xlb_lattice_t`` for these words (``words_ptr``: a device copy; default the
+        host array).  The segment table stays host memory owned by this object."""
+        from . import _cabi
+
+        lat = _cabi.Lattice(self.words.ctypes.data if words_ptr is None else words_ptr, self.words.size,
+                            self.chunk_words, self.n_chunks, self.n_elements, self.flags)
+        if self.segments is not None:
+            lat.n_segments = int(self.segments.shape[0])
+            lat.segments = self.segments.ctypes.data
+        return lat
 
     @property
     def nbytes(self):
@@ -493,12 +509,20 @@ def _try_merge(live, pos):
     return _pack_merged_block(k1, idx1, a1, k2, idx2, a2, drift), i
 
 
+SEG_MAIN, SEG_BB6D = 0, 1
+
+
 def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True, fuse=True,
-              merge=True):
+              merge=True, split_lenses=True):
     """Pack ``elements`` (the ``Line.elements`` list).  ``element_index`` in every record
     is the position in that list, so ``at_element`` matches the reference's indexing even
     though exact no-ops (zero-length drifts, all-zero multipoles, disabled lenses) are not
-    emitted."""
+    emitted.
+
+    ``split_lenses`` (fast encoding only): every BeamBeam6D record gets a chunk of its own
+    and the lattice becomes a sequence of segments -- tracking-kernel segments separated by
+    6D-lens segments (``xlb_lattice_t::segments``) -- so that the tracking kernels need not
+    carry the register-hungry 6D lens."""
     assert chunk_words % 2 == 0 and chunk_words >= 16
     monitors = dict(layout=[], words=0)
     recs = []
@@ -521,7 +545,7 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
                        0, idx, d.length)
             rec.w.extend([plain.w[1], plain.w[2]])  # r21, r43 as evaluated for the plain record
             counts[rec.tag] = counts.get(rec.tag, 0) + 1
-            recs.append(rec.words())
+            recs.append((rec.tag, rec.words()))
             continue
         merged = _try_merge(live, pos - 1) if (fuse and merge and not strict and name == "Multipole") else None
         if merged is not None:
@@ -540,34 +564,49 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
         else:
             rec = _pack_element(el, idx, strict, monitors)
         tag = rec.tag
-        if tag in (T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D):
-            flags |= F_BEAMFIELDS
-            if tag == T_BEAMBEAM6D:
-                flags |= F_BB6D
         counts[tag] = counts.get(tag, 0) + 1
-        recs.append(rec.words())
-    biggest = max([len(r) for r in recs] + [0])
+        recs.append((tag, rec.words()))
+    split = bool(split_lenses) and not strict and any(t == T_BEAMBEAM6D for t, _ in recs)
+    for tag, _ in recs:
+        if tag == T_BEAMBEAM6D:
+            flags |= F_BB6D
+        if tag in (T_BEAMBEAM4D, T_SPACECHARGE) or (tag == T_BEAMBEAM6D and not split):
+            flags |= F_BEAMFIELDS
+    biggest = max([len(r) for _, r in recs] + [0])
     while biggest + 2 > chunk_words:
         chunk_words *= 2
     if chunk_words * 8 > 96 * 1024:
         raise ValueError("an element record (%d words) exceeds the 96 KiB chunk limit" % biggest)
-    chunks = []
-    cur = []
-    for r in recs:
+    chunks = []    # (words, is last chunk of its segment)
+    segments = []  # [first_chunk, n_chunks, kind]
+
+    def close_segment(cur, first, kind):
+        cur += [_hdr(T_END_TURN, 0, 0), np.uint64(0)]
+        chunks.append((cur, True))
+        segments.append([first, len(chunks) - first, kind])
+
+    cur, first = [], 0
+    for tag, r in recs:
+        if split and tag == T_BEAMBEAM6D:
+            if cur or len(chunks) > first:  # a tracking segment precedes the lens
+                close_segment(cur, first, SEG_MAIN)
+            close_segment(list(r), len(chunks), SEG_BB6D)
+            cur, first = [], len(chunks)
+            continue
         if len(cur) + len(r) + 2 > chunk_words:
             cur += [_hdr(T_END_CHUNK, 0, 0), np.uint64(0)]
-            chunks.append(cur)
+            chunks.append((cur, False))
             cur = []
         cur = cur + r
-    cur += [_hdr(T_END_TURN, 0, 0), np.uint64(0)]
-    chunks.append(cur)
+    close_segment(cur, first, SEG_MAIN)  # the closing tracking segment (may be empty) counts the turn
     words = np.zeros(len(chunks) * chunk_words, dtype=np.uint64)
-    for i, ch in enumerate(chunks):
+    for i, (ch, last) in enumerate(chunks):
         words[i * chunk_words: i * chunk_words + len(ch)] = np.array(ch, dtype=np.uint64)
         # fill the tail with END_CHUNK/END_TURN so a stray read can never run away
-        tail = _hdr(T_END_TURN if i == len(chunks) - 1 else T_END_CHUNK, 0, 0)
+        tail = _hdr(T_END_TURN if last else T_END_CHUNK, 0, 0)
         words[i * chunk_words + len(ch): (i + 1) * chunk_words: 2] = tail
-    return PackedLattice(words, chunk_words, len(chunks), len(elements), flags, monitors, counts)
+    seg = np.array(segments, dtype=np.int32).reshape(-1, 3) if split else None
+    return PackedLattice(words, chunk_words, len(chunks), len(elements), flags, monitors, counts, seg)
 
 
 def element_specs(elements):

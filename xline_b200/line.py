@@ -37,6 +37,7 @@ class Line(E.Element):
         self.fuse_records = True  # pack-time peephole: multipole -> aperture -> drift in one record
         self.chunk_words = None   # 8-byte words per TMA chunk (None = lattice.DEFAULT_CHUNK_WORDS)
         self.merge_multipoles = True  # fast encoding: co-located thin multipoles become one kick
+        self.split_lenses = True      # fast encoding: BeamBeam6D lenses run as kernels of their own
         self._monitor_buf = None
         self.loss_tally = None
         self.last_stats = None
@@ -252,17 +253,16 @@ class Line(E.Element):
         """Host-side packed lattice (``lattice.PackedLattice``), cached."""
         if chunk_words is None:
             chunk_words = self.chunk_words
-        key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles,
+        key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles, self.split_lenses,
                getattr(self, "_keep_noops", False), tuple(map(id, self.elements)))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
         kw = {} if chunk_words is None else {"chunk_words": chunk_words}
         packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records,
-                           merge=self.merge_multipoles,
+                           merge=self.merge_multipoles, split_lenses=self.split_lenses,
                            drop_noops=not getattr(self, "_keep_noops", False), **kw)
-        lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
-                            packed.n_chunks, packed.n_elements, packed.flags)
+        lat = packed.c_lattice()
         _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))
         self._cache["host_%d" % strict] = (key, packed)
         return packed
@@ -297,8 +297,7 @@ class Line(E.Element):
             n = len(p)
             if n == 0 or num_turns == 0:
                 return None
-            lat = _cabi.Lattice(words.data_ptr(), words.numel(), packed.chunk_words, packed.n_chunks,
-                                packed.n_elements, packed.flags)
+            lat = packed.c_lattice(words.data_ptr())
             cols = {}
             for k, t in p._columns():
                 if not t.is_contiguous():
@@ -321,7 +320,7 @@ class Line(E.Element):
                 # are best with 1)
                 nbf = sum(v for k, v in packed.record_counts.items() if k in (16, 17, 18))
                 sparse = nbf < 0.05 * max(sum(packed.record_counts.values()), 1)
-                dense_ppt = 1 if packed.record_counts.get(18, 0) else 2
+                dense_ppt = 1 if (packed.record_counts.get(18, 0) and packed.segments is None) else 2
                 particles_per_thread, threads_per_block = ((3, threads_per_block or 128) if sparse
                                                            else (dense_ppt, threads_per_block or 256))
             opts = _cabi.TrackOptions()
@@ -371,8 +370,8 @@ class Line(E.Element):
         (no record fusing, no merging, no-ops kept) so every element owns a row."""
         n = len(p)
         k = n if max_particles is None else min(int(max_particles), n)
-        saved = (self.fuse_records, self.merge_multipoles, self._cache)
-        self.fuse_records, self.merge_multipoles, self._cache = False, False, {}
+        saved = (self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache)
+        self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache = False, False, False, {}
         self._keep_noops = True
         try:
             trace = torch.full((len(self) + 1, 6, k), float("nan"), dtype=torch.float64, device=p.device)
@@ -381,7 +380,7 @@ class Line(E.Element):
             self.track(p, num_turns=1, strict=strict, _trace=trace[1:])
         finally:
             self._keep_noops = False
-            self.fuse_records, self.merge_multipoles, self._cache = saved
+            self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache = saved
         return trace
 
     def track_elem_by_elem(self, p, start=True, end=False):
