@@ -315,7 +315,7 @@ class Line(E.Element):
             if particles_per_thread == 0 and (packed.flags & 2) and not strict:
                 # beam-field lattice: the thin-lens records still dominate when lenses are
                 # sparse (LHC + 74 lenses: 3 particles/thread wins); dense space-charge
-                # lattices prefer fewer (PS Booster with 120 kicks/turn: 1.57e8 / 1.69e8 / 1.26e8
+                # lattices prefer fewer (PS Booster with 120 kicks/turn: 1.57e8 / 1.91e8 / 1.59e8
                 # particle-turns/s for 1 / 2 / 3; the kernels that carry the 6D lens spill and
                 # are best with 1)
                 nbf = sum(v for k, v in packed.record_counts.items() if k in (16, 17, 18))
