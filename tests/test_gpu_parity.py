@@ -350,6 +350,27 @@ def test_sharding_invariance_full_size():
     assert 0 < lost.sum() < n
 
 
+@pytest.mark.parametrize("config", ["lhc", "petra4"])
+def test_kernel_variants_agree_bitwise(config):
+    """Every compiled (particles per thread, threads per block) variant of the fast kernel gives
+    the same bits: the fast maps spell their FMAs out, so no instantiation is free to fuse a
+    different product of a sum of products (csrc/track_impl.cuh, el_drift)."""
+    from xline_b200 import configs
+
+    n = 60_000
+    line, cols, p0c, m0 = (configs.config_lhc if config == "lhc" else configs.config_petra4)(n)
+    ref = None
+    for ppt, thr in ((3, 128), (1, 128), (1, 256), (1, 512), (2, 128), (2, 256), (4, 128)):
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=2, particles_per_thread=ppt, threads_per_block=thr)
+        cur = p.to_numpy()
+        if ref is None:
+            ref = cur
+            continue
+        for k in ref:
+            assert np.array_equal(ref[k], cur[k], equal_nan=True), (k, ppt, thr)
+
+
 def test_track_refuses_cpu_particles():
     import xline_b200 as xl
 
