@@ -552,6 +552,31 @@ def test_lhc_beambeam_c3_one_turn_against_oracle():
         assert H.scaled_err(got[k], ref[k]) <= FAST_FULL_TURN_TOL, (k, H.scaled_err(got[k], ref[k]))
 
 
+def test_lhc_beambeam_c3_unstable_particles_go_non_finite_like_the_oracle():
+    """The C3 lattice has no apertures: a particle far outside the dynamic aperture is never
+    removed, its coordinates overflow and it stays in the beam as NaN -- in the reference's
+    NumPy path and here alike.  The 64 highest-amplitude particles of the 1 M-particle C3 beam,
+    10 turns: the same particles (one, particle 948 199) end non-finite, nobody is lost."""
+    from xline_b200 import configs
+
+    line, cols, p0c, m0 = configs.config_lhc_beambeam(1_000_000)
+    amp = np.hypot(cols["x"] / 2e-4, cols["y"] / 2e-4) + np.hypot(cols["px"] / 2e-6, cols["py"] / 2e-6)
+    idx = np.argsort(-amp)[:64]
+    sub = {k: np.ascontiguousarray(v[idx]) for k, v in cols.items()}
+    p = make_particles(sub, p0c, m0)
+    line.track(p, num_turns=10)
+    got = p.to_numpy()
+    with np.errstate(all="ignore"):
+        ref = H.run_oracle(line.to_specs(), {k: v for k, v in sub.items() if k != "particle_id"}, p0c, m0,
+                           num_turns=10)
+    bad_got = ~np.isfinite(got["x"])
+    bad_ref = ~np.isfinite(ref["x"])
+    assert np.array_equal(bad_got, bad_ref), (idx[bad_got], idx[bad_ref])
+    assert 948_199 in idx[bad_ref]
+    assert np.array_equal(got["state"], ref["state"]) and (got["state"] == 1).all()
+    assert np.array_equal(got["at_turn"], ref["at_turn"])
+
+
 def test_psb_like_c5_space_charge_and_monitor_against_oracle():
     """C5 stand-in (xline_b200.configs.config_psb_like): 128 SCQGaussProfile kicks per turn,
     DipoleEdge, curved dipoles, the PSB aperture mix, a cavity and a BeamMonitor."""
