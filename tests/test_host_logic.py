@@ -246,14 +246,16 @@ def test_algorithmic_ops_match_oracle_count():
 
 
 def test_product_package_never_imports_the_oracle():
-    """The oracle is test infrastructure: nothing under xline_b200/ may import or execute it."""
-    pkg = os.path.join(ROOT, "xline_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
-                txt = open(os.path.join(dirpath, fn)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
-                assert "xline_oracle" not in txt and "ref_harness" not in txt, fn
+    """The oracle is test infrastructure: nothing under xline_b200/ or scripts/ may import or
+    execute it (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do)."""
+    for top in ("xline_b200", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
+                    txt = open(os.path.join(dirpath, fn)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+                    assert "xline_oracle" not in txt and "ref_harness" not in txt, fn
+                    assert "run_oracle" not in txt, fn
 
 
 def test_missing_library_fails_loudly(monkeypatch):
