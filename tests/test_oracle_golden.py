@@ -138,3 +138,46 @@ def test_monitor_store_index():
     assert [xo.monitor_store_index(f, t) for t in range(10)] == [-1, -1, 0, -1, 1, -1, 2, -1, -1, -1]
     f["is_rolling"] = True
     assert xo.monitor_store_index(f, 8) == 0
+
+
+@pytest.mark.parametrize("p0c,mass0", [(450e9, 938.27208816e6), (0.571e9, 938.27208816e6), (6e9, 0.51099895e6)])
+def test_restated_energy_bookkeeping_is_relativistic_kinematics(p0c, mass0):
+    """`add_to_energy` and the `delta` setter belong to the unvendored `xpart` container and are
+    restated from memory (the part of the oracle the reference's own tests do not pin).  What
+    they must compute is fixed by kinematics, independently of any implementation: with
+    pc = p0c (1 + delta) and E = sqrt(pc^2 + m^2), adding dE gives E' = E + dE,
+    pc' = sqrt(E'^2 - m^2), delta' = pc'/p0c - 1, rpp' = p0c/pc', rvv' = (pc'/E')/beta0 and
+    zeta' = zeta rvv'/rvv.  Checked in 80-bit arithmetic for the oracle and for the host-side
+    `xline_b200.Particles` (protons at 450 GeV and at PS Booster energy, electrons at 6 GeV)."""
+    import torch
+
+    import xline_b200 as xl
+
+    L = np.longdouble
+    rng = np.random.default_rng(5)
+    n = 4000
+    delta = rng.normal(0, 3e-3, n)
+    zeta = rng.normal(0, 0.1, n)
+    d_e = rng.normal(0, 1e-4, n) * p0c  # up to a few 1e-4 of the momentum per kick
+    m, p0 = L(mass0), L(p0c)
+    e0 = np.sqrt(p0 * p0 + m * m)
+    beta0 = p0 / e0
+    pc = p0 * (1 + delta.astype(L))
+    en = np.sqrt(pc * pc + m * m)
+    rvv_before = (pc / en) / beta0
+    en2 = en + d_e.astype(L)
+    pc2 = np.sqrt(en2 * en2 - m * m)
+    want = dict(delta=pc2 / p0 - 1, rpp=p0 / pc2, rvv=(pc2 / en2) / beta0)
+    want["zeta"] = zeta.astype(L) * want["rvv"] / rvv_before
+
+    o = xo.OracleParticles(n, p0c=p0c, mass0=mass0, zeta=zeta, delta=delta)
+    assert np.max(np.abs(o.rvv - rvv_before.astype(np.float64))) <= 2e-15
+    o.add_to_energy(d_e)
+    p = xl.Particles(p0c=p0c, mass0=mass0, device="cpu", zeta=zeta, delta=delta)
+    p.add_to_energy(torch.as_tensor(d_e))
+    for k, w in want.items():
+        w64 = w.astype(np.float64)
+        scale = np.max(np.abs(w64)) if k in ("delta", "zeta") else 1.0
+        # sqrt(1 + small) - 1 loses the bits of `small` below 1e-16: absolute, not relative, accuracy
+        assert np.max(np.abs(getattr(o, k) - w64)) <= 4e-15 * max(scale, 1.0), k
+        assert np.max(np.abs(getattr(p, k).numpy() - w64)) <= 4e-15 * max(scale, 1.0), k
