@@ -1,0 +1,315 @@
+"""TEST INFRASTRUCTURE -- a NumPy interpreter of the packed lattice format.
+
+Walks the 8-byte words produced by ``xline_b200.lattice.pack_line`` exactly as
+``include/xline_b200.h`` documents them (chunks, record headers, the thin / merged / edge block
+families, both encodings) and applies the element maps with plain NumPy arithmetic.  It exists
+so that the packer and the format can be checked on a machine without a GPU
+(``tests/test_packed_format.py``): a lattice packed in the *strict* encoding and interpreted
+here must reproduce the oracle bit for bit (NumPy has no FMA contraction, and the strict
+encoding keeps the reference's operation order), the *fast* encoding to rounding.
+
+Thin-lens tags only (no BeamMonitor, BeamBeam, space charge, RFMultipole): those are covered
+by the GPU parity tests.  Nothing in the product imports this file.
+"""
+import numpy as np
+
+T_END_TURN, T_END_CHUNK, T_DRIFT, T_DRIFT_EXACT, T_MULTIPOLE, T_MULTIPOLE_CURVED = range(6)
+T_CAVITY, T_RFMULTIPOLE, T_XYSHIFT, T_SROTATION, T_DIPOLE_EDGE = range(6, 11)
+T_LIMIT_RECT, T_LIMIT_ELLIPSE, T_LIMIT_RECT_ELLIPSE, T_MONITOR, T_SAWTOOTH_CAVITY = range(11, 16)
+AP_NONE, AP_RECT_SYM, AP_RECT, AP_ELLIPSE = range(4)
+COORDS = ("x", "px", "y", "py", "zeta", "delta", "rpp", "rvv")
+
+
+class _Beam:
+    """Fixed-length arrays with a state flag, like the device side: lost particles stay where
+    they were lost (``state = 0``, ``at_element``, ``at_turn`` set)."""
+
+    def __init__(self, cols, p0c, mass0, q0=1.0):
+        n = len(cols["x"])
+        self.n = n
+        self.q0, self.p0c, self.mass0 = float(q0), float(p0c), float(mass0)
+        self.energy0 = float(np.sqrt(self.p0c * self.p0c + self.mass0 * self.mass0))
+        self.beta0 = self.p0c / self.energy0
+        for k in ("x", "px", "y", "py", "zeta"):
+            setattr(self, k, np.array(cols.get(k, np.zeros(n)), dtype=np.float64))
+        self.chi = np.ones(n)
+        self.charge_ratio = np.ones(n)
+        d = np.array(cols.get("delta", np.zeros(n)), dtype=np.float64)
+        db0 = d * self.beta0
+        ptaub0 = np.sqrt(db0 ** 2 + 2 * db0 * self.beta0 + 1) - 1
+        self.delta = d
+        self.rvv = (1 + d) / (1 + ptaub0)
+        self.rpp = 1 / (1 + d)
+        self.state = np.ones(n, dtype=np.int64)
+        self.at_element = np.zeros(n, dtype=np.int64)
+        self.at_turn = np.zeros(n, dtype=np.int64)
+
+    def result(self):
+        return {k: getattr(self, k).copy() for k in COORDS + ("state", "at_element", "at_turn")}
+
+
+class _Live:
+    """The alive particles of a beam as working copies; ``commit`` writes them back, ``lose``
+    freezes a subset as it is now."""
+
+    def __init__(self, beam):
+        self.beam = beam
+        self.idx = np.flatnonzero(beam.state == 1)
+        for k in COORDS + ("chi", "charge_ratio"):
+            setattr(self, k, getattr(beam, k)[self.idx].copy())
+
+    def __len__(self):
+        return len(self.idx)
+
+    def commit(self):
+        for k in COORDS:
+            getattr(self.beam, k)[self.idx] = getattr(self, k)
+
+    def lose(self, lost, elem_idx, turn, override=None):
+        """``lost``: boolean over the live set.  ``override``: {name: array over the live set}
+        of values the lost particles are frozen with instead of the current ones."""
+        if not lost.any():
+            return
+        gone = self.idx[lost]
+        for k in COORDS:
+            src = override[k] if override and k in override else getattr(self, k)
+            getattr(self.beam, k)[gone] = src[lost]
+        self.beam.state[gone] = 0
+        self.beam.at_element[gone] = elem_idx
+        self.beam.at_turn[gone] = turn
+        keep = ~lost
+        self.idx = self.idx[keep]
+        for k in COORDS + ("chi", "charge_ratio"):
+            setattr(self, k, getattr(self, k)[keep])
+
+
+def _add_to_energy(p, beam, energy):  # Pyparticles.add_to_energy as restated in the oracle
+    b0 = beam.beta0
+    old_rvv = p.rvv
+    db0 = p.delta * b0
+    ptaub0 = np.sqrt(db0 ** 2 + 2 * db0 * b0 + 1) - 1
+    ptaub0 = ptaub0 + energy / beam.energy0
+    ptau = ptaub0 / b0
+    p.delta = np.sqrt(ptau ** 2 + 2 * ptau / b0 + 1) - 1
+    opd = 1 + p.delta
+    p.rvv = opd / (1 + ptaub0)
+    p.rpp = 1 / opd
+    p.zeta = p.zeta * (p.rvv / old_rvv)
+
+
+def _drift(p, L):
+    xp = p.px * p.rpp
+    yp = p.py * p.rpp
+    p.x = p.x + xp * L
+    p.y = p.y + yp * L
+    p.zeta = p.zeta + L * (p.rvv - (1 + (xp ** 2 + yp ** 2) / 2))
+
+
+def _drift_exact(p, L):
+    opd = 1 + p.delta
+    lpzi = L / np.sqrt(opd ** 2 - p.px ** 2 - p.py ** 2)
+    p.x = p.x + p.px * lpzi
+    p.y = p.y + p.py * lpzi
+    p.zeta = p.zeta + (p.rvv * L - opd * lpzi)
+
+
+def _closing_drift(p, tag, L):
+    if tag & 8:
+        if tag & 16:
+            _drift_exact(p, L)
+        else:
+            _drift(p, L)
+
+
+def _horner(p, pairs, order, strict):
+    """pairs[m] = (kn, ks)[order - m]; strict: raw knl/ksl and the division by ii at every
+    step; fast: coefficients already divided by i!."""
+    dpx = pairs[0, 0]
+    dpy = pairs[0, 1]
+    for ii in range(order, 0, -1):
+        k = pairs[order - ii + 1]
+        zre = dpx * p.x - dpy * p.y
+        zim = dpx * p.y + dpy * p.x
+        if strict:
+            zre = zre / ii
+            zim = zim / ii
+        dpx = k[0] + zre
+        dpy = k[1] + zim
+    one = np.ones_like(p.x)
+    return dpx * one, dpy * one  # arrays also for order 0 (x * 1.0 is exact)
+
+
+def _kick(p, dpx, dpy, curved, strict, k0=None):
+    """Returns (new px, new py, new zeta) of a thin multipole (elements.py:135-156).
+    ``curved`` = (hxl, hyl, length, 1/length) or None; ``k0`` = (knl[0], ksl[0]) used by the
+    curvature terms."""
+    ddx = -p.chi * dpx
+    ddy = p.chi * dpy
+    zeta = p.zeta
+    if curved is not None:
+        hxl, hyl, length, inv_length = curved
+        b1l = p.chi * k0[0]
+        a1l = p.chi * k0[1]
+        hxlx = hxl * p.x
+        hyly = hyl * p.y
+        if strict:
+            if length > 0:
+                hxx = hxlx / length
+                hyy = hyly / length
+            else:
+                hxx = 0
+                hyy = 0
+        else:
+            hxx = hxlx * inv_length
+            hyy = hyly * inv_length
+        ddx = ddx + (hxl + hxl * p.delta - b1l * hxx)
+        ddy = ddy - (hyl + hyl * p.delta - a1l * hyy)
+        zeta = p.zeta - p.chi * (hxlx - hyly)
+    return p.px + ddx, p.py + ddy, zeta
+
+
+def _inside(kind, x, y, lim, strict):
+    if kind == AP_RECT_SYM:
+        return (np.abs(x) <= lim[1]) & (np.abs(y) <= lim[3])
+    if kind == AP_RECT:
+        return (x >= lim[0]) & (x <= lim[1]) & (y >= lim[2]) & (y <= lim[3])
+    if strict:
+        return x * x / lim[0] + y * y / lim[1] <= 1.0
+    return x * x * lim[2] + y * y * lim[3] <= 1.0
+
+
+def track(packed, cols, p0c, mass0, num_turns=1):
+    """Interpret ``packed`` (a PackedLattice without segments) for ``num_turns`` turns."""
+    assert packed.segments is None
+    words = np.ascontiguousarray(packed.words, dtype=np.uint64)
+    f64 = words.view(np.float64)
+    i64 = words.view(np.int64)
+    strict = packed.strict
+    beam = _Beam(cols, p0c, mass0)
+    cw = packed.chunk_words
+    for turn in range(num_turns):
+        p = _Live(beam)
+        done = False
+        for ch in range(packed.n_chunks):
+            if done:
+                break
+            w = ch * cw
+            while True:
+                hdr = int(words[w])
+                tag, aux, size, elem = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0xFFFF, hdr >> 32
+                assert w % 2 == 0 and w + 2 * size <= (ch + 1) * cw, "record straddles a chunk"
+                p0 = f64[w + 1]
+                pair = lambda m, _w=w: f64[_w + 2 * m: _w + 2 * m + 2]  # noqa: E731
+                nxt = w + 2 * size
+                if tag == T_END_CHUNK:
+                    break
+                if tag == T_END_TURN:
+                    done = True
+                    break
+                if len(p) == 0:
+                    w = nxt
+                    continue
+                if (tag & 0xC0) == 0x80:  # thin (0x80) or merged (0xA0) block
+                    merged = bool(tag & 0x20)
+                    assert not (merged and strict)
+                    order = aux
+                    pairs = f64[w + 4: w + 4 + 2 * (order + 1)].reshape(order + 1, 2)
+                    t = 2 + order + 1  # pair index of what follows the coefficients
+                    dpx, dpy = _horner(p, pairs, order, strict)
+                    ap = tag & 3
+                    if not merged:
+                        curved = None
+                        if tag & 4:
+                            curved = (pair(t)[0], pair(t)[1], pair(t + 1)[0], pair(t + 1)[1])
+                            t += 2
+                        p.px, p.py, p.zeta = _kick(p, dpx, dpy, curved, strict, k0=pairs[order])
+                        if ap != AP_NONE:
+                            lim = np.concatenate([pair(t), pair(t + 1)])
+                            p.lose(~_inside(ap, p.x, p.y, lim, strict), int(i64[w + 2]), turn)
+                    else:
+                        idxs, info = int(i64[w + 2]), int(i64[w + 3])
+                        a1_idx, a2_idx = idxs & 0xFFFFFFFF, idxs >> 32
+                        k1_order, has_a1 = info & 0xFF, (info >> 8) & 1
+                        curved = k0 = None
+                        if tag & 4:
+                            curved = (pair(t)[0], pair(t)[1], pair(t + 1)[0], pair(t + 1)[1])
+                            k0 = pair(t + 2)
+                            t += 3
+                        npx, npy, nzeta = _kick(p, dpx, dpy, curved, False, k0=k0)
+                        if has_a1:  # lost at A1: frozen with K1's kick only
+                            lim = np.concatenate([pair(t), pair(t + 1)])
+                            t += 2
+                            lost = ~_inside(AP_ELLIPSE, p.x, p.y, lim, False)
+                            if lost.any():
+                                k1_pairs_at = t + (2 if ap != AP_NONE else 0)
+                                k1 = f64[w + 2 * k1_pairs_at: w + 2 * (k1_pairs_at + k1_order + 1)].reshape(-1, 2)
+                                kx, ky = _horner(p, k1, k1_order, False)
+                                frozen = dict(px=p.px + (-p.chi * kx), py=p.py + p.chi * ky)
+                                keep = ~lost
+                                p.lose(lost, a1_idx, turn, override=frozen)
+                                npx, npy, nzeta = npx[keep], npy[keep], nzeta[keep]
+                        p.px, p.py, p.zeta = npx, npy, nzeta
+                        if ap != AP_NONE:
+                            lim = np.concatenate([pair(t), pair(t + 1)])
+                            p.lose(~_inside(ap, p.x, p.y, lim, False), a2_idx, turn)
+                    _closing_drift(p, tag, p0)
+                elif (tag & 0xC0) == 0xC0:  # dipole edge -> [drift]
+                    e = pair(1)
+                    p.px = p.px + e[0] * p.x
+                    p.py = p.py + e[1] * p.y
+                    _closing_drift(p, tag, p0)
+                elif tag == T_DRIFT:
+                    _drift(p, p0)
+                elif tag == T_DRIFT_EXACT:
+                    _drift_exact(p, p0)
+                elif tag == T_MULTIPOLE:
+                    pairs = f64[w + 2: w + 2 + 2 * (aux + 1)].reshape(aux + 1, 2)
+                    dpx, dpy = _horner(p, pairs, aux, strict)
+                    p.px, p.py, p.zeta = _kick(p, dpx, dpy, None, strict)
+                elif tag == T_MULTIPOLE_CURVED:
+                    pairs = f64[w + 6: w + 6 + 2 * (aux + 1)].reshape(aux + 1, 2)
+                    dpx, dpy = _horner(p, pairs, aux, strict)
+                    curved = (p0, pair(1)[0], pair(1)[1], pair(2)[0])
+                    p.px, p.py, p.zeta = _kick(p, dpx, dpy, curved, strict, k0=pairs[aux])
+                elif tag in (T_CAVITY, T_SAWTOOTH_CAVITY):
+                    k, lag = pair(1)
+                    tau = p.zeta / p.rvv / beam.beta0
+                    phase = lag - k * tau
+                    if tag == T_CAVITY:
+                        wave = np.sin(phase)
+                    else:
+                        wave = (phase + np.pi) % (2 * np.pi) - np.pi
+                    _add_to_energy(p, beam, p.charge_ratio * beam.q0 * p0 * wave)
+                elif tag == T_XYSHIFT:
+                    p.x = p.x - p0
+                    p.y = p.y - pair(1)[0]
+                elif tag == T_SROTATION:
+                    cz, sz = p0, pair(1)[0]
+                    xn = cz * p.x + sz * p.y
+                    yn = -sz * p.x + cz * p.y
+                    p.x, p.y = xn, yn
+                    xn = cz * p.px + sz * p.py
+                    yn = -sz * p.px + cz * p.py
+                    p.px, p.py = xn, yn
+                elif tag == T_DIPOLE_EDGE:
+                    p.px = p.px + p0 * p.x
+                    p.py = p.py + pair(1)[0] * p.y
+                elif tag == T_LIMIT_RECT:
+                    lim = np.array([p0, pair(1)[0], pair(1)[1], pair(2)[0]])
+                    p.lose(~_inside(AP_RECT_SYM if aux else AP_RECT, p.x, p.y, lim, strict), elem, turn)
+                elif tag == T_LIMIT_ELLIPSE:
+                    lim = np.array([p0, pair(1)[0], pair(1)[1], pair(2)[0]])
+                    p.lose(~_inside(AP_ELLIPSE, p.x, p.y, lim, strict), elem, turn)
+                elif tag == T_LIMIT_RECT_ELLIPSE:
+                    mx, my = p0, pair(1)[0]
+                    lim = np.array([pair(1)[1], pair(2)[0], pair(2)[1], pair(3)[0]])
+                    inside = ((p.x >= -mx) & (p.x <= mx) & (p.y >= -my) & (p.y <= my)
+                              & _inside(AP_ELLIPSE, p.x, p.y, lim, strict))
+                    p.lose(~inside, elem, turn)
+                else:
+                    raise NotImplementedError("tag 0x%02x is outside the interpreter's scope" % tag)
+                w = nxt
+        assert done, "lattice without END_TURN"
+        p.commit()
+        beam.at_turn[p.idx] += 1
+    return beam.result()
