@@ -58,12 +58,6 @@ XLB_DEF_VARIANT(2, 128, 3)
 XLB_DEF_VARIANT(2, 256, 2)
 XLB_DEF_VARIANT(3, 128, 3)
 XLB_DEF_VARIANT(4, 128, 2)
-// Candidate for the next measurement round, opt-in only (particles_per_thread = 4,
-// threads_per_block = 96): four particles per thread at the occupancy of the default (4 CTAs x
-// 3 warps = 12 warps/SM, 168 registers).  ptxas spills 152 B around the record header and in
-// the loss paths (~7 local-memory instructions per record) against 8 % fewer instructions per
-// particle than 3 particles per thread.  Not yet timed on a B200.
-XLB_DEF_VARIANT(4, 96, 4)
 
 #if XLB_BEAMFIELDS
 #define XLB_TABLE fast_bf_table
@@ -82,7 +76,6 @@ static const Variant XLB_TABLE[] = {
     XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_SUFFIX, 2, 256, 2),
     XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 3),
     XLB_VARIANT_ENTRY("fast/ppt4/t128" XLB_SUFFIX, 4, 128, 2),
-    XLB_VARIANT_ENTRY("fast/ppt4/t96" XLB_SUFFIX, 4, 96, 4),
     XLB_TRACE_ENTRY("fast/trace"),
 };
 const Variant *XLB_TABLE_FN(int *n) {
