@@ -8,8 +8,8 @@ so that the packer and the format can be checked on a machine without a GPU
 here must reproduce the oracle bit for bit (NumPy has no FMA contraction, and the strict
 encoding keeps the reference's operation order), the *fast* encoding to rounding.
 
-Thin-lens tags only (no BeamMonitor, BeamBeam, space charge, RFMultipole): those are covered
-by the GPU parity tests.  Nothing in the product imports this file.
+Everything but the beam-field records (BeamBeam4D/6D, space charge): those are covered by the
+GPU parity tests.  Nothing in the product imports this file.
 """
 import numpy as np
 
@@ -43,6 +43,7 @@ class _Beam:
         self.state = np.ones(n, dtype=np.int64)
         self.at_element = np.zeros(n, dtype=np.int64)
         self.at_turn = np.zeros(n, dtype=np.int64)
+        self.particle_id = np.arange(n, dtype=np.int64)
 
     def result(self):
         return {k: getattr(self, k).copy() for k in COORDS + ("state", "at_element", "at_turn")}
@@ -178,8 +179,10 @@ def _inside(kind, x, y, lim, strict):
     return x * x * lim[2] + y * y * lim[3] <= 1.0
 
 
-def track(packed, cols, p0c, mass0, num_turns=1):
-    """Interpret ``packed`` (a PackedLattice without segments) for ``num_turns`` turns."""
+def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
+    """Interpret ``packed`` (a PackedLattice without segments) for ``num_turns`` turns.
+    ``monitor``: fp64 array of ``packed.monitor_words`` words (NaN-filled by the caller), the
+    BeamMonitor storage of include/xline_b200.h: per monitor [7 fields][num_stores][n_ids]."""
     assert packed.segments is None
     words = np.ascontiguousarray(packed.words, dtype=np.uint64)
     f64 = words.view(np.float64)
@@ -306,6 +309,43 @@ def track(packed, cols, p0c, mass0, num_turns=1):
                     inside = ((p.x >= -mx) & (p.x <= mx) & (p.y >= -my) & (p.y <= my)
                               & _inside(AP_ELLIPSE, p.x, p.y, lim, strict))
                     p.lose(~inside, elem, turn)
+                elif tag == T_RFMULTIPOLE:  # [hdr,V][k,lag] then per order [knl,ksl][pn,ps]
+                    k, lag = pair(1)
+                    ktau = k * (p.zeta / p.rvv / beam.beta0)
+                    dpx = dpy = dptr = 0
+                    zre, zim = 1, 0
+                    for ii in range(aux + 1):
+                        kn, ks = pair(2 + 2 * ii)
+                        pn, ps = pair(3 + 2 * ii)
+                        cn, sn = np.cos(pn - ktau), np.sin(pn - ktau)
+                        cs, ss = np.cos(ps - ktau), np.sin(ps - ktau)
+                        dpx = dpx + (cn * kn * zre - cs * ks * zim)
+                        dpy = dpy + (cs * ks * zre + cn * kn * zim)
+                        zret = (zre * p.x - zim * p.y) / (ii + 1)
+                        zim = (zim * p.x + zre * p.y) / (ii + 1)
+                        zre = zret
+                        dptr = dptr + (sn * (kn * zre) - ss * (ks * zim))
+                    p.px = p.px + -p.chi * dpx
+                    p.py = p.py + p.chi * dpy
+                    dv0 = p0 * np.sin(lag - ktau)
+                    _add_to_energy(p, beam, p.charge_ratio * beam.q0 * (dv0 - beam.p0c * k * dptr))
+                elif tag == T_MONITOR:  # [hdr,0][start,skip][num_stores,min_id][max_id,rolling][offset,0]
+                    start, skip, num_stores, min_id = (int(v) for v in i64[w + 2: w + 6])
+                    max_id, rolling, off = (int(v) for v in i64[w + 6: w + 9])
+                    nn = max_id - min_id + 1
+                    if monitor is not None and nn > 0 and num_stores > 0 and turn >= start \
+                            and (turn - start) % skip == 0:
+                        st = (turn - start) // skip
+                        if st >= num_stores and rolling:
+                            st %= num_stores
+                        if st < num_stores:
+                            pid = beam.particle_id[p.idx]
+                            sel = (pid >= min_id) & (pid <= max_id)
+                            plane = num_stores * nn
+                            o = off + st * nn + (pid[sel] - min_id)
+                            for f, name in enumerate(("x", "px", "y", "py", "zeta", "delta")):
+                                monitor[o + f * plane] = getattr(p, name)[sel]
+                            monitor[o + 6 * plane] = float(turn)
                 else:
                     raise NotImplementedError("tag 0x%02x is outside the interpreter's scope" % tag)
                 w = nxt

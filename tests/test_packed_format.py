@@ -94,3 +94,44 @@ def test_fast_lhc_lattice_uses_every_block_family():
             tags.add(tag)
             w += 2 * size
     assert {0x8D, 0x88, 0x89, 0x8B, 0xA9} <= tags, sorted(hex(t) for t in tags)
+
+
+def test_rfmultipole_and_monitor_records():
+    """RFMultipole (strict: the oracle bit for bit) and the BeamMonitor record: slot arithmetic
+    of elements.py:497-524 and the [7 fields][num_stores][n_ids] storage layout, with skip,
+    a particle-id window, losses in between and a rolling monitor."""
+    import xline_b200 as xl
+
+    n, turns = 300, 9
+    rng = np.random.default_rng(21)
+    cols = dict(x=rng.normal(0, 1e-3, n), px=rng.normal(0, 1e-4, n), y=rng.normal(0, 1e-3, n),
+                py=rng.normal(0, 1e-4, n), zeta=rng.normal(0, 0.05, n), delta=rng.normal(0, 3e-4, n))
+    mon = xl.BeamMonitor(num_stores=3, start=2, skip=2, min_particle_id=10, max_particle_id=259)
+    roll = xl.BeamMonitor(num_stores=2, start=0, skip=1, min_particle_id=0, max_particle_id=n - 1, is_rolling=True)
+    line = xl.Line([
+        xl.Drift(length=1.0), xl.Multipole(knl=[0, 0.3]), xl.LimitEllipse(a=3e-3, b=3e-3), mon,
+        xl.RFMultipole(voltage=2e5, frequency=4e8, lag=30.0, knl=[1e-4, 0.02, 0.5], ksl=[0, 0.01],
+                       pn=[10.0, 20.0, 0.0], ps=[0.0, 45.0]),
+        xl.Drift(length=2.0), xl.Multipole(knl=[0, -0.3]), roll, xl.Cavity(voltage=1e6, frequency=4e8, lag=180),
+    ])
+    p0c, m0 = 450e9, 938.27208816e6
+    packed = line.pack(strict=True)
+    buf = np.full(packed.monitor_words, np.nan)
+    got = PI.track(packed, cols, p0c, m0, num_turns=turns, monitor=buf)
+    stores = {}
+    ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=turns, monitors=stores)
+    assert (ref["state"] == 0).any()
+    for k in ("state", "at_element", "at_turn"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in H.COORDS:
+        assert np.array_equal(got[k], ref[k]), k
+    for slot in packed.monitor_layout:
+        want = stores[slot["element_index"]]
+        ns, nn = slot["num_stores"], slot["nn"]
+        view = buf[slot["offset"]: slot["offset"] + 7 * ns * nn].reshape(7, ns, nn)
+        written = want["at_turn"] >= 0
+        assert written.any() and not written.all()
+        for f, k in enumerate(("x", "px", "y", "py", "zeta", "delta")):
+            assert np.array_equal(np.isnan(view[f]), ~written), k
+            assert np.array_equal(view[f][written], want[k][written]), k
+        assert np.array_equal(view[6][written], want["at_turn"][written].astype(float))
