@@ -9,6 +9,7 @@ turn; state / at_element / at_turn bit-exact except for particles within EDGE_EP
 aperture edge (none of the cases below has one unless stated).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -868,3 +869,31 @@ def test_work_queue_with_strict_kernel_and_monitor():
     for k in ma:
         assert torch.equal(torch.nan_to_num(ma[k], nan=-7.0), torch.nan_to_num(mb[k], nan=-7.0)), k
     assert int((~torch.isnan(ma["x"])).sum()) > 1000
+
+
+@pytest.mark.skipif(not os.environ.get("XLB_GPU_FUZZ"),
+                    reason="opt-in (XLB_GPU_FUZZ=1): written after the round's GPU budget was spent, not yet run on a B200")
+@pytest.mark.parametrize("seed", range(40))
+def test_random_lines_on_the_gpu(seed):
+    """The packer fuzz of tests/test_packed_format.py through the kernels: random thin-lens lines
+    (every block shape, merged records, small chunks, losses), three turns, strict and fast
+    kernels against the oracle."""
+    from tests.test_packed_format import _random_line
+
+    rng = np.random.default_rng(1000 + seed)
+    line = _random_line(rng)
+    line.chunk_words = int(rng.choice([32, 64, 256]))
+    n = 150
+    cols = dict(x=rng.normal(0, 8e-4, n), px=rng.normal(0, 1e-4, n), y=rng.normal(0, 8e-4, n),
+                py=rng.normal(0, 1e-4, n), zeta=rng.normal(0, 0.05, n), delta=rng.normal(0, 3e-4, n))
+    p0c, m0 = 26e9, 938.27208816e6
+    with np.errstate(all="ignore"):
+        ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=3)
+    for strict in (True, False):
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=3, strict=strict)
+        got = p.to_numpy()
+        for k in ("state", "at_element", "at_turn"):
+            assert np.array_equal(got[k], ref[k]), (k, strict)
+        for k in H.COORDS:
+            assert H.scaled_err(got[k], ref[k]) <= (1e-13 if strict else 1e-10), (k, strict)
