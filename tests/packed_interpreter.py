@@ -8,14 +8,15 @@ so that the packer and the format can be checked on a machine without a GPU
 here must reproduce the oracle bit for bit (NumPy has no FMA contraction, and the strict
 encoding keeps the reference's operation order), the *fast* encoding to rounding.
 
-Everything but the beam-field records (BeamBeam4D/6D, space charge): those are covered by the
-GPU parity tests.  Nothing in the product imports this file.
+Everything but the BeamBeam6D record (covered by the GPU parity tests); the Faddeeva function of
+the Gaussian-field records is scipy's.  Nothing in the product imports this file.
 """
 import numpy as np
 
 T_END_TURN, T_END_CHUNK, T_DRIFT, T_DRIFT_EXACT, T_MULTIPOLE, T_MULTIPOLE_CURVED = range(6)
 T_CAVITY, T_RFMULTIPOLE, T_XYSHIFT, T_SROTATION, T_DIPOLE_EDGE = range(6, 11)
 T_LIMIT_RECT, T_LIMIT_ELLIPSE, T_LIMIT_RECT_ELLIPSE, T_MONITOR, T_SAWTOOTH_CAVITY = range(11, 16)
+T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D = 16, 17, 18
 AP_NONE, AP_RECT_SYM, AP_RECT, AP_ELLIPSE = range(4)
 COORDS = ("x", "px", "y", "py", "zeta", "delta", "rpp", "rvv")
 
@@ -177,6 +178,47 @@ def _inside(kind, x, y, lim, strict):
     if strict:
         return x * x / lim[0] + y * y / lim[1] <= 1.0
     return x * x * lim[2] + y * y * lim[3] <= 1.0
+
+
+def _gauss_field(f64, i64, w, x, y, strict):
+    """Field block at word ``w``: [sx,sy][i64 kind,0][A,0] and, in the fast encoding,
+    [1/S, A sqrt(pi)/S][small/big, big/small][1/(2 big^2), 1/(2 small^2)]
+    (gaussian_fields.py:5-21 round, :29-99 Bassetti-Erskine).  Returns Ex, Ey and the number of
+    pairs the block occupies."""
+    from scipy.special import wofz
+
+    sx, sy = f64[w], f64[w + 1]
+    kind = int(i64[w + 2])
+    A = f64[w + 4]
+    npairs = 3 if strict else 6
+    if kind == 0:
+        sigma = 0.5 * (sx + sy)
+        r2 = x * x + y * y
+        with np.errstate(all="ignore"):
+            temp = np.where(r2 < 1e-20, np.sqrt(r2) * A / sigma,
+                            (1.0 - np.exp(-0.5 * r2 / (sigma * sigma))) * A / np.where(r2 > 0, r2, 1.0))
+        return temp * x, temp * y, npairs
+    wide = kind == 1
+    u, v = (np.abs(x), np.abs(y)) if wide else (np.abs(y), np.abs(x))  # along big, along small
+    if strict:
+        big, small = (sx, sy) if wide else (sy, sx)
+        S = np.sqrt(2.0 * (big * big - small * small))
+        fact = A * 1.772453850905516 / S
+        w1 = wofz((u + 1j * v) / S)
+        w2 = wofz((small / big * u + 1j * (big / small * v)) / S)
+        e = np.exp(-u * u / (2.0 * big * big) - v * v / (2.0 * small * small))
+    else:
+        inv_s, fact = f64[w + 6], f64[w + 7]
+        r_sb, r_bs = f64[w + 8], f64[w + 9]
+        h_big, h_small = f64[w + 10], f64[w + 11]
+        us, vs = u * inv_s, v * inv_s
+        w1 = wofz(us + 1j * vs)
+        w2 = wofz(r_sb * us + 1j * (r_bs * vs))
+        e = np.exp(-(u * u * h_big + v * v * h_small))
+    f_im = fact * (w1.imag - w2.imag * e)  # field along the big axis
+    f_re = fact * (w1.real - w2.real * e)  # field along the small axis
+    ex, ey = (f_im, f_re) if wide else (f_re, f_im)
+    return np.where(x < 0, -ex, ex), np.where(y < 0, -ey, ey), npairs
 
 
 def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
@@ -346,6 +388,44 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                             for f, name in enumerate(("x", "px", "y", "py", "zeta", "delta")):
                                 monitor[o + f * plane] = getattr(p, name)[sel]
                             monitor[o + 6 * plane] = float(turn)
+                elif tag == T_BEAMBEAM4D:  # [hdr,0][x_bb,y_bb] field [d_px,d_py][beta_r, charge*qe]
+                    ex, ey, nf = _gauss_field(f64, i64, w + 4, p.x - pair(1)[0], p.y - pair(1)[1], strict)
+                    d, bc = pair(2 + nf), pair(3 + nf)
+                    beta = beam.beta0 / p.rvv  # sic, beambeam.py:55
+                    fact = p.chi * bc[1] * (p.charge_ratio * beam.q0) * (1.0 + beta * bc[0]) / (beam.p0c * (beta + bc[0]))
+                    p.px = p.px + (fact * ex - d[0])
+                    p.py = p.py + (fact * ey - d[1])
+                elif tag == T_SPACECHARGE:  # [hdr,0][x_co,y_co] field [base, p1] ...; aux = profile kind
+                    ex, ey, nf = _gauss_field(f64, i64, w + 4, p.x - pair(1)[0], p.y - pair(1)[1], strict)
+                    t = w + 2 * (2 + nf)  # first word after the field block
+                    base, p1 = f64[t], f64[t + 1]
+                    common = beam.q0 * beam.q0 * (1.0 - beam.beta0 * beam.beta0) / (beam.p0c * beam.beta0) * base
+                    lam = 1.0
+                    if aux == 1:  # q-Gaussian in zeta / rvv: [sqrt_beta/cq, 1-q][1/(1-q), 0][i64 gauss, 0]
+                        arg = p1 * (p.zeta / p.rvv) ** 2
+                        if int(i64[t + 6]):
+                            lam = f64[t + 2] * np.exp(-arg)
+                        else:
+                            up = np.maximum(1.0 + (-arg) * f64[t + 3], 0.0)
+                            lam = f64[t + 2] * up ** f64[t + 4]
+                    elif aux in (2, 3):  # [base,z0][dz,0][i64 n,0] then the profile / the spline
+                        z0, dz, npts = p1, f64[t + 2], int(i64[t + 4])
+                        i = np.clip(np.floor((p.zeta - z0) / dz).astype(np.int64), 0, npts - 2)
+                        if aux == 2:
+                            prof = f64[t + 6: t + 6 + npts]
+                            xi = z0 + i * dz
+                            lam = (prof[i + 1] - prof[i]) / dz * (p.zeta - xi) + prof[i]
+                            lam = np.where(p.zeta <= z0, prof[0], lam)
+                            lam = np.where(p.zeta >= z0 + (npts - 1) * dz, prof[npts - 1], lam)
+                        else:
+                            xk = f64[t + 6: t + 6 + npts]
+                            c = f64[t + 6 + npts: t + 6 + npts + 4 * (npts - 1)]
+                            m = npts - 1
+                            dt = p.zeta - xk[i]
+                            lam = ((c[i] * dt + c[m + i]) * dt + c[2 * m + i]) * dt + c[3 * m + i]
+                    fact = p.chi * p.charge_ratio * common * lam
+                    p.px = p.px + fact * ex
+                    p.py = p.py + fact * ey
                 else:
                     raise NotImplementedError("tag 0x%02x is outside the interpreter's scope" % tag)
                 w = nxt

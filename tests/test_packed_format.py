@@ -227,3 +227,53 @@ def test_random_lines_strict_bitwise_and_fast_close(seed):
         assert np.array_equal(fast[k], ref[k]), k
     for k in H.COORDS:
         assert H.scaled_err(fast[k], ref[k]) <= 1e-10, (k, H.scaled_err(fast[k], ref[k]))
+
+
+def test_beam_field_records():
+    """BeamBeam4D and the three space-charge elements (round and both elliptical orientations,
+    q-Gaussian profiles with q = 1, > 1 and < 1, linear and cubic-spline line densities): record
+    layouts and the constants the fast encoding folds at pack time, against the oracle."""
+    import xline_b200 as xl
+
+    n = 400
+    rng = np.random.default_rng(33)
+    cols = dict(x=rng.normal(0, 2e-3, n), px=rng.normal(0, 1e-4, n), y=rng.normal(0, 2e-3, n),
+                py=rng.normal(0, 1e-4, n), zeta=rng.normal(0, 0.4, n), delta=rng.normal(0, 1e-3, n))
+    cols["x"][:3] = [0.0, 1e-12, -1e-3]  # on axis / inside the linearised core / negative quadrant
+    cols["y"][:3] = [0.0, 0.0, -2e-3]
+    prof = np.exp(-0.5 * (np.linspace(-1.5, 1.5, 31) / 0.5) ** 2)
+    line = xl.Line([
+        xl.BeamBeam4D(charge=1e11, sigma_x=1.2e-3, sigma_y=0.7e-3, beta_r=0.9, x_bb=1e-4, y_bb=-2e-4, d_px=1e-7, d_py=-2e-7),
+        xl.Drift(length=1.0),
+        xl.BeamBeam4D(charge=-8e10, sigma_x=0.6e-3, sigma_y=1.5e-3, beta_r=1.0),
+        xl.BeamBeam4D(charge=5e10, sigma_x=1.0e-3, sigma_y=1.0e-3 * (1 + 1e-12), beta_r=1.0),  # round branch
+        xl.Multipole(knl=[0, 0.1]), xl.Drift(length=0.5),
+        xl.SCCoasting(number_of_particles=3e12, circumference=157.0, sigma_x=2e-3, sigma_y=1e-3, length=3.0,
+                      x_co=1e-4, y_co=2e-4),
+        xl.SCQGaussProfile(number_of_particles=1e11, bunchlength_rms=0.4, sigma_x=1e-3, sigma_y=2.5e-3, length=2.0,
+                           q_parameter=1.0),
+        xl.SCQGaussProfile(number_of_particles=1e11, bunchlength_rms=0.4, sigma_x=1.5e-3, sigma_y=1.5e-3, length=2.0,
+                           q_parameter=1.3),
+        xl.SCQGaussProfile(number_of_particles=1e11, bunchlength_rms=0.4, sigma_x=2e-3, sigma_y=1.5e-3, length=2.0,
+                           q_parameter=0.7),
+        xl.Drift(length=0.7),
+        xl.SCInterpolatedProfile(number_of_particles=2e11, line_density_profile=prof.tolist(), dz=0.1, z0=-1.5,
+                                 sigma_x=1.1e-3, sigma_y=0.9e-3, length=1.5, method=0),
+        xl.SCInterpolatedProfile(number_of_particles=2e11, line_density_profile=prof.tolist(), dz=0.1, z0=-1.5,
+                                 sigma_x=0.9e-3, sigma_y=1.4e-3, length=1.5, method=1),
+        xl.LimitEllipse(a=8e-3, b=8e-3),
+    ])
+    p0c, m0 = 0.571e9, 938.27208816e6  # PS Booster momentum: space charge matters there
+    with np.errstate(all="ignore"):
+        ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=2)
+    kick = np.sqrt(np.mean((ref["px"] - cols["px"]) ** 2))
+    assert kick > 1e-7, "the lattice must actually kick"
+    for strict in (True, False):
+        packed = line.pack(strict=strict)
+        assert packed.flags & 2  # XLB_F_BEAMFIELDS
+        with np.errstate(all="ignore"):
+            got = PI.track(packed, cols, p0c, m0, num_turns=2)
+        for k in ("state", "at_element", "at_turn"):
+            assert np.array_equal(got[k], ref[k]), (k, strict)
+        for k in H.COORDS:
+            assert H.scaled_err(got[k], ref[k]) <= 1e-12, (k, strict, H.scaled_err(got[k], ref[k]))
