@@ -277,3 +277,34 @@ def test_beam_field_records():
             assert np.array_equal(got[k], ref[k]), (k, strict)
         for k in H.COORDS:
             assert H.scaled_err(got[k], ref[k]) <= 1e-12, (k, strict, H.scaled_err(got[k], ref[k]))
+
+
+def test_psb_c5_lattice_interpreted():
+    """The real C5 lattice (PS Booster: 120 space-charge kicks, 264 apertures of three kinds,
+    RF, one BeamMonitor) through the format interpreter, two turns, with particles pushed into
+    the apertures: both encodings against the oracle, monitor contents included."""
+    n, turns = 96, 2
+    line, cols, p0c, m0 = configs.config_psb(n, monitor_stores=turns, monitor_ids=n)
+    cols = {k: np.array(v) for k, v in cols.items() if k != "particle_id"}
+    cols["x"][::7] *= 12.0  # some beyond the vacuum chamber
+    cols["y"][3::11] *= 15.0
+    stores = {}
+    with np.errstate(all="ignore"):
+        ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=turns, monitors=stores)
+    assert 0 < (ref["state"] == 0).sum() < n
+    for strict in (True, False):
+        packed = line.pack(strict=strict)
+        buf = np.full(packed.monitor_words, np.nan)
+        with np.errstate(all="ignore"):
+            got = PI.track(packed, cols, p0c, m0, num_turns=turns, monitor=buf)
+        for k in ("state", "at_element", "at_turn"):
+            assert np.array_equal(got[k], ref[k]), (k, strict)
+        for k in H.COORDS:
+            assert H.scaled_err(got[k], ref[k]) <= 1e-11, (k, strict, H.scaled_err(got[k], ref[k]))
+        (slot,) = packed.monitor_layout
+        want = stores[slot["element_index"]]
+        view = buf[slot["offset"]: slot["offset"] + 7 * slot["num_stores"] * slot["nn"]].reshape(7, slot["num_stores"], slot["nn"])
+        written = want["at_turn"] >= 0
+        assert np.array_equal(np.isnan(view[0]), ~written)
+        for f, k in enumerate(("x", "px", "y", "py", "zeta", "delta")):
+            assert H.scaled_err(view[f][written], want[k][written]) <= 1e-11, (k, strict)
