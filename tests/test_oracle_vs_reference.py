@@ -56,3 +56,30 @@ def test_golden_fixtures_are_current():
     ref = run_reference(specs, cols, m["p0c"], m["mass0"], chi=chi, charge_ratio=chi)
     for k in H.COORDS:
         assert np.array_equal(ref[k], out[k])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_thin_lens_lines_bitwise(seed):
+    """The random lines of the packer fuzz (tests/test_packed_format.py) through the REAL
+    reference element code: the oracle must agree bit for bit on everything but the sin() of
+    the cavities evaluated through the reference's scalar path (<= 4e-16)."""
+    from oracle.make_golden import run_reference
+    from tests.test_packed_format import _random_line
+
+    rng = np.random.default_rng(1000 + seed)
+    line = _random_line(rng)
+    n = 150
+    cols = dict(x=rng.normal(0, 8e-4, n), px=rng.normal(0, 1e-4, n), y=rng.normal(0, 8e-4, n),
+                py=rng.normal(0, 1e-4, n), zeta=rng.normal(0, 0.05, n), delta=rng.normal(0, 3e-4, n))
+    specs = line.to_specs()
+    with np.errstate(all="ignore"):
+        ref = run_reference(specs, cols, 26e9, 938.27208816e6, num_turns=3)
+        got = H.run_oracle(specs, cols, 26e9, 938.27208816e6, num_turns=3)
+    for k in ("state", "at_element", "at_turn"):
+        assert np.array_equal(got[k], ref[k]), k
+    has_cavity = any(name == "Cavity" for name, _ in specs)
+    for k in H.COORDS:
+        if has_cavity:
+            assert H.rel_err(got[k], ref[k]) <= 1e-13, k  # a last-ulp sin() difference, carried through 3 turns
+        else:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
