@@ -234,6 +234,17 @@ int xlb_measure_fp64_peak(int repeats, double *flops_out, double *ms_out);
  * (cycles_per_dfma[0..3]); the first is the dependent-issue latency of the FP64 pipe. */
 int xlb_measure_dfma_latency(double *cycles_per_dfma, int n);
 
+/* Device self-test of the strict kernels' division sequences (csrc/track_impl.cuh: reciprocal
+ * from the record or the constant table + FMA remainder corrections in place of the IEEE
+ * division subroutine; the reference divides at xline/elements.py:130-134, 143-144, 436):
+ * every quotient is compared bit for bit with the device's own a / b.  mode 0: integer divisors
+ * 1..255 (the Horner step), mode 1: arbitrary positive divisors (`length`, a*a, b*b).  Dividends:
+ * random sign and mantissa, exponents uniform in 2^+-exponent_span, every 16th next to a
+ * rounding midpoint of the quotient.  *mismatches must come back 0. */
+int xlb_selftest_exact_division(const double *divisors, int n_divisors, int mode,
+                                int samples_per_thread, uint64_t seed, int exponent_span,
+                                uint64_t *mismatches, uint64_t *samples);
+
 /* Number of tracking-kernel variants compiled in, and a description of variant i
  * ("fast/ppt2/lean", ...) with its register count -- build introspection for tests. */
 int xlb_kernel_variant_count(void);

@@ -15,7 +15,7 @@ EXPORTS = (
     "xlb_abi_version", "xlb_last_error", "xlb_lattice_validate", "xlb_track_device",
     "xlb_track_device_timed", "xlb_track_host", "xlb_get_stats", "xlb_compact_alive_device",
     "xlb_measure_fp64_peak", "xlb_measure_dfma_latency", "xlb_kernel_variant_count",
-    "xlb_kernel_variant_info",
+    "xlb_kernel_variant_info", "xlb_selftest_exact_division",
 )
 
 
@@ -123,6 +123,19 @@ def measure_dfma_latency():
     L.xlb_measure_dfma_latency.argtypes = [C.POINTER(C.c_double), C.c_int]
     check(L.xlb_measure_dfma_latency(out, 4))
     return dict(zip((1, 2, 4, 8), [float(v) for v in out]))
+
+
+def selftest_exact_division(divisors, mode, samples_per_thread=64, seed=1, exponent_span=200):
+    """(mismatches, samples) of the strict kernels' division sequences against the device's own
+    IEEE division (``xlb_selftest_exact_division``)."""
+    L = lib()
+    L.xlb_selftest_exact_division.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                              C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    arr = (C.c_double * len(divisors))(*[float(v) for v in divisors])
+    bad, n = C.c_uint64(0), C.c_uint64(0)
+    check(L.xlb_selftest_exact_division(arr, len(divisors), int(mode), int(samples_per_thread), int(seed),
+                                        int(exponent_span), C.byref(bad), C.byref(n)))
+    return bad.value, n.value
 
 
 def measure_fp64_peak(repeats=5):

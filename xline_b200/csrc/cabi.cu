@@ -807,6 +807,34 @@ int xlb_measure_dfma_latency(double *cycles_per_dfma, int n) {
   return rc;
 }
 
+int xlb_selftest_exact_division(const double *divisors, int n_divisors, int mode, int samples_per_thread,
+                                uint64_t seed, int exponent_span, uint64_t *mismatches, uint64_t *samples) {
+  if (!divisors || n_divisors < 1 || !mismatches || samples_per_thread < 1 || exponent_span < 0 ||
+      exponent_span > 900 || (mode != 0 && mode != 1))
+    return fail(XLB_EINVAL, "bad argument");
+  for (int i = 0; i < n_divisors; ++i) {
+    const double b = divisors[i];
+    if (mode == 0 && !(b >= 1 && b <= 255 && b == static_cast<double>(static_cast<int>(b))))
+      return fail(XLB_EINVAL, "mode 0 takes integer divisors 1..255");
+    if (!(b > 0) || b > 1e150 || b < 1e-150) return fail(XLB_EINVAL, "divisor out of range");
+  }
+  double *d = nullptr;
+  unsigned long long *dm = nullptr;
+  XLB_CUDA(cudaMalloc(&d, sizeof(double) * n_divisors));
+  XLB_CUDA(cudaMalloc(&dm, sizeof(unsigned long long)));
+  XLB_CUDA(cudaMemcpy(d, divisors, sizeof(double) * n_divisors, cudaMemcpyHostToDevice));
+  XLB_CUDA(cudaMemset(dm, 0, sizeof(unsigned long long)));
+  const int rc = strict_selftest_division(d, n_divisors, mode, samples_per_thread, seed, exponent_span, dm, nullptr);
+  if (rc != 0) return fail(XLB_ECUDA, cudaGetErrorString(static_cast<cudaError_t>(rc)));
+  unsigned long long h = 0;
+  XLB_CUDA(cudaMemcpy(&h, dm, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  cudaFree(dm);
+  *mismatches = h;
+  if (samples) *samples = 148ull * 4 * 256 * static_cast<unsigned long long>(samples_per_thread) * n_divisors;
+  return XLB_OK;
+}
+
 int xlb_kernel_variant_count(void) {
   int a = 0, b = 0, c = 0, d = 0, e = 0;
   fast_variants(&a);

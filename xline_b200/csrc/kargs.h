@@ -48,6 +48,11 @@ struct Variant {
 // `rec` = the BEAMBEAM6D record in the device copy of the lattice.
 void fast_bb6d_launch(const KArgs &a, const unsigned long long *rec, int blocks, int threads, void *stream);
 
+// Device self-test of the strict kernels' division sequences (track_strict.cu).
+int strict_selftest_division(const double *d_divisors, int n_div, int mode, int per_thread,
+                             unsigned long long seed, int span, unsigned long long *d_mismatches,
+                             void *stream);
+
 const Variant *fast_variants(int *n);
 const Variant *strict_variants(int *n);
 
