@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XLB_ABI_VERSION 2
+#define XLB_ABI_VERSION 3
 
 /* error codes */
 #define XLB_OK 0
@@ -173,14 +173,23 @@ typedef struct xlb_track_options {
                                 turns than this, over more particle blocks than the device
                                 holds at once, runs persistent CTAs that pull (particle block,
                                 turn segment) items.  0 = default (5), < 0 = off          */
-  int32_t reserved;
+  int32_t flags;             /* XLB_OPT_* below                                          */
   double *trace;             /* optional element-by-element trace, [n_elements][6][trace_particles]
                                 fp64 (x px y py zeta delta after every element for the first
                                 trace_particles particle slots; the device form of
                                 Line.track_elem_by_elem, xline/line.py:97-108).  Needs
                                 num_turns == 1 and a lattice packed without record fusing     */
   int64_t trace_particles;
+  int64_t element_index_offset; /* added to the element index recorded in at_element (not to the
+                                loss-tally index): a caller that pushes the elements of a Line
+                                one call at a time -- el.track(p) in a loop, the reference's
+                                track_elem_by_elem (xline/line.py:97-108) -- passes the position
+                                of the element in that Line                                 */
 } xlb_track_options_t;
+
+#define XLB_OPT_NO_TURN_COUNT 1 /* do not advance at_turn at the end of the lattice: the call is
+                                   one element (or a part) of a turn, like the reference's
+                                   el.track(p), which never touches the turn counter          */
 
 /* Statistics of the last xlb_track_* call on this thread. */
 typedef struct xlb_track_stats {

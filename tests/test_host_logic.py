@@ -189,7 +189,7 @@ def test_cabi_exports_every_declared_symbol():
     L = _cabi.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.xlb_abi_version() == _cabi.ABI_VERSION == 2
+    assert L.xlb_abi_version() == _cabi.ABI_VERSION == 3
     # argument validation happens before any CUDA call
     assert L.xlb_track_device(None, None, None, None) == -1
     assert b"null" in L.xlb_last_error()
@@ -416,3 +416,41 @@ def test_pack_segments_lattices_with_6d_lenses(tmp_path):
     lat = pk.c_lattice()
     lat.flags = pk.flags & ~lattice.F_BB6D
     assert L.xlb_lattice_validate(C.byref(lat)) != 0 and b"XLB_F_BB6D" in L.xlb_last_error()
+
+
+def test_edit_tracking_repacks_only_when_something_changed():
+    """element fields edited in place must reach the packed lattice; an untouched
+    line must not be re-packed (the check is O(1) while the global edit clock stands still)."""
+    from xline_b200 import elements as E
+
+    line = xl.Line([xl.Multipole(knl=[0.0, 1e-3]), xl.Drift(length=1.0), xl.Cavity(voltage=1e6, frequency=4e8)])
+    a = line.pack()
+    assert line.pack() is a and line.pack(strict=True) is line.pack(strict=True)
+    clock = E.edit_clock()
+    assert line.pack() is a and E.edit_clock() == clock
+    xl.Drift(length=3.0)  # an unrelated element is created: clock moves, this line is unchanged
+    assert line.pack() is a
+    line.elements[2].voltage = 2e6
+    b = line.pack()
+    assert b is not a and not np.array_equal(a.words, b.words)
+    line.elements[0].knl[1] = 2e-3
+    c = line.pack()
+    assert c is not b and not np.array_equal(c.words, b.words)
+    line.elements[0].ksl = np.array([0.0, 1e-4])
+    d = line.pack()
+    line.elements[0].ksl *= 2.0
+    e = line.pack()
+    assert d is not c and e is not d and not np.array_equal(d.words, e.words)
+    line.elements.append(xl.Drift(length=0.5))
+    f = line.pack()
+    assert f is not e and f.n_elements == 4
+    line.elements += [xl.Drift(length=0.25)]
+    assert line.pack().n_elements == 5
+    line.fuse_records = False
+    assert line.pack() is not f
+    # element values own their data: the caller's list is copied on assignment
+    mine = [0.0, 5e-3]
+    m = xl.Multipole(knl=mine)
+    mine[1] = 7.0
+    assert m.knl[1] == 5e-3 and m.to_dict()["knl"] == [0.0, 5e-3] and type(m.to_dict()["knl"]) is list
+    assert m.copy() == m and xl.Multipole.from_dict(m.to_dict()) == m

@@ -341,3 +341,87 @@ def test_optics_thin_fodo_known_answer():
                         xl.Drift(length=half), xl.Multipole(knl=[0, kf / 2])])
     kf, kd = optics.match_tunes(build, (0.35, -0.35), tw["qx"], tw["qy"])
     assert kf == pytest.approx(1 / f, rel=1e-8) and kd == pytest.approx(-1 / f, rel=1e-8)
+
+
+def _hl_like_sequence():
+    """Hand-built thin sequence with the element kinds of an HL-LHC job: RF multipole, crab
+    cavities (horizontal and vertical), beam-beam markers (4D, 6D) and an octagon aperture."""
+    from types import SimpleNamespace
+
+    from xline_b200.madx_input import MadElement, MadSequence
+
+    els = [
+        MadElement("rfm", "rfmultipole", dict(volt=1.5, freq=400.0, lag=0.25, knl=[0.0, 1e-3], ksl=[0.0, 2e-4],
+                                              pnl=[0.0, 0.1], psl=[0.0, 0.2]), 1.0),
+        MadElement("crab_h", "crabcavity", dict(volt=3.4, freq=400.79, lag=0.0, tilt=0.0), 2.0),
+        MadElement("crab_v", "crabcavity", dict(volt=3.4, freq=400.79, lag=0.5, tilt=math.pi / 2), 3.0),
+        MadElement("bb_ho", "beambeam", dict(slot_id=6), 4.0),
+        MadElement("bb_lr", "beambeam", dict(slot_id=4), 5.0),
+        MadElement("bb_ho60", "beambeam", dict(slot_id=60), 5.5),
+        MadElement("mq", "multipole", dict(knl=[0.0, 1e-3], ksl=[0.0, 0.0], lrad=0.5, apertype="octagon",
+                                           aperture=[0.02, 0.018, 0.5, 1.0]), 6.0),
+        MadElement("skipme", "instrument", dict(l=0.0), 7.0),
+    ]
+    return MadSequence("hl", 8.0, els, SimpleNamespace(pc=7000.0))
+
+
+def test_rf_crab_beambeam_octagon_mappings():
+    """xline/loader_mad.py:97-170, 229-242 (RFMultipole, crab cavity with skiptilt, beam-beam
+    placeholders by slot id, octagon -> LimitPolygon)."""
+    seq = _hl_like_sequence()
+    out = dict(iter_from_madx_sequence(seq, xl.elements.element_classes(), install_apertures=True))
+    rfm = out["rfm"]
+    assert isinstance(rfm, xl.RFMultipole) and rfm.voltage == 1.5e6 and rfm.frequency == 400e6 and rfm.lag == 90.0
+    assert list(rfm.pn) == [0.0, 36.0] and list(rfm.ps) == [0.0, 72.0]
+    h, v = out["crab_h"], out["crab_v"]
+    assert list(h.knl) == [3.4 / 7000.0 * 1e-3] and list(h.pn) == [90.0]
+    assert list(v.ksl) == [-3.4 / 7000.0 * 1e-3] and list(v.ps) == [0.5 * 360 + 90]
+    assert "crab_v_pretilt" not in out  # skiptilt
+    assert isinstance(out["bb_ho"], xl.BeamBeam6D) and isinstance(out["bb_ho60"], xl.BeamBeam6D)
+    assert isinstance(out["bb_lr"], xl.BeamBeam4D)
+    poly = out["mq_aperture"]
+    assert type(poly).__name__ == "LimitPolygon" and len(poly.x_vertices) == 8
+    assert poly.x_vertices[0] == 0.02 and poly.y_vertices[1] == 0.018
+    # an ignored type is skipped, not yielded as None
+    names = [n for n, _ in iter_from_madx_sequence(seq, xl.elements.element_classes(),
+                                                   ignored_madtypes=["beambeam"])]
+    assert "bb_ho" not in names and "rfm" in names
+    # a line holding a LimitPolygon refuses to track like the reference (elements.py:483)
+    with pytest.raises(NotImplementedError):
+        xl.Line([poly]).pack()
+    # Elens: parameters only, readable from the reference's dictionaries
+    d = {"elements": [{"__class__": "Elens", "voltage": 1e4, "current": 5.0, "inner_radius": 1e-3,
+                       "outer_radius": 2e-3, "ebeam_center_x": 0.0, "ebeam_center_y": 0.0, "elens_length": 3.0}],
+         "element_names": ["el"]}
+    ln = xl.Line.from_dict(d)
+    assert ln.elements[0].current == 5.0
+    with pytest.raises(ValueError):
+        ln.pack()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/xline"), reason="reference tree absent")
+def test_rf_crab_beambeam_octagon_mappings_against_reference_loader():
+    import importlib
+    import sys
+    import types
+
+    from oracle import ref_harness as rh
+
+    els = rh.load_reference()
+    pkg = sys.modules.get("xline")
+    if pkg is None or not hasattr(pkg, "__path__"):
+        stub = types.ModuleType("xline")
+        stub.__path__ = [os.path.join(rh.REFERENCE_ROOT, "xline")]
+        sys.modules["xline"] = stub
+    ref_loader = importlib.import_module("xline.loader_mad")
+    seq = _hl_like_sequence()
+    mine = list(iter_from_madx_sequence(seq, xl.elements.element_classes(), install_apertures=True))
+    theirs = list(ref_loader.iter_from_madx_sequence(seq, classes=els, install_apertures=True))
+    assert [n for n, _ in mine] == [n for n, _ in theirs]
+    for (_, a), (_, b) in zip(mine, theirs):
+        assert type(a).__name__ == type(b).__name__
+        da, db = a.to_dict(keepextra=False), b.to_dict(keepextra=False)
+        assert set(da) == set(db), (type(a).__name__, set(da) ^ set(db))
+        for k in da:
+            if k != "__class__":
+                assert np.array_equal(np.asarray(da[k], dtype=float), np.asarray(db[k], dtype=float)), k

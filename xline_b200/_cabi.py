@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxline_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+OPT_NO_TURN_COUNT = 1  # xlb_track_options_t::flags
 
 EXPORTS = (
     "xlb_abi_version", "xlb_last_error", "xlb_lattice_validate", "xlb_track_device",
@@ -45,8 +46,8 @@ class TrackOptions(C.Structure):
         ("num_turns", C.c_int32), ("particles_per_thread", C.c_int32),
         ("threads_per_block", C.c_int32), ("turns_per_launch", C.c_int32),
         ("loss_tally", C.c_void_p), ("monitor_data", C.c_void_p), ("monitor_words", C.c_int64),
-        ("compact_threshold", C.c_double), ("turns_per_item", C.c_int32), ("reserved", C.c_int32),
-        ("trace", C.c_void_p), ("trace_particles", C.c_int64),
+        ("compact_threshold", C.c_double), ("turns_per_item", C.c_int32), ("flags", C.c_int32),
+        ("trace", C.c_void_p), ("trace_particles", C.c_int64), ("element_index_offset", C.c_int64),
     ]
 
 

@@ -149,6 +149,14 @@ struct Scratch {
   size_t arena_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // One call at a time per device: the queue, the survivor list, the counters and the pinned
+  // read-back words above are shared by every xlb_track_* call on this GPU.  Host threads
+  // serialise on `call_mu` (recursive: the host entry point calls the device one); work that a
+  // previous call left running on ANOTHER stream is ordered before the next call's by `done`,
+  // recorded at the end of every call and waited for at the start of the next.
+  std::recursive_mutex call_mu;
+  cudaEvent_t done = nullptr;
+  bool have_done = false;
 };
 static std::mutex g_mu;
 static std::vector<Scratch *> g_scratch;
@@ -170,6 +178,7 @@ static int get_scratch(Scratch **out) {
   XLB_CUDA(cudaMallocHost(&s->h_pinned, 2 * sizeof(unsigned int)));
   XLB_CUDA(cudaEventCreate(&s->ev0));
   XLB_CUDA(cudaEventCreate(&s->ev1));
+  XLB_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
   g_scratch.push_back(s);
   *out = s;
   return XLB_OK;
@@ -304,10 +313,11 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
   const bool split = lat->n_segments > 1;  // 6D lenses run as kernels of their own
   const bool bb6d = (lat->flags & XLB_F_BB6D) != 0 && !split;
-  // defaults from the B200 sweep (scripts/probe_bench_sweep.py): thin-lens lattices run best
-  // with 3 particles per thread in 128-thread CTAs (3 CTAs/SM, 164 registers, no spills)
-  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread
-                                                  : ((strict || beamfields) ? 2 : 3);
+  // defaults from the B200 sweeps (scripts/probe_bench_sweep.py, scripts/probe_strict.py):
+  // thin-lens lattices run best with 3 particles per thread in 128-thread CTAs (3 CTAs/SM,
+  // 162 / 164 registers fast / strict, no spills); strict C2: 1.08e7 particle-turns/s against
+  // 9.1e6 (2 x 128), 7.3e6 (1 x 256), 6.7e6 (2 x 256)
+  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread : (beamfields ? 2 : 3);
   const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (ppt_req == 3 ? 128 : 256);
   const bool trace = o->trace != nullptr;
   if (trace && (o->num_turns != 1 || o->trace_particles < 1))
@@ -323,6 +333,15 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
 
   Scratch *s = nullptr;
   if ((rc = get_scratch(&s)) != XLB_OK) return rc;
+  std::lock_guard<std::recursive_mutex> call_lock(s->call_mu);
+  if (s->have_done) XLB_CUDA(cudaStreamWaitEvent(st, s->done, 0));
+  struct DoneMark {  // whatever way the call ends, later calls wait for what it enqueued
+    Scratch *s;
+    cudaStream_t st;
+    ~DoneMark() {
+      if (cudaEventRecord(s->done, st) == cudaSuccess) s->have_done = true;
+    }
+  } done_mark{s, st};
 
   const size_t chunk_bytes = static_cast<size_t>(lat->chunk_words) * 8;
   const size_t smem = XLB_STAGES * chunk_bytes + (2 * XLB_STAGES + 2) * sizeof(unsigned long long);
@@ -349,6 +368,8 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.n_lost = s->n_lost;
   a.trace = o->trace;
   a.trace_n = o->trace_particles;
+  a.elem_off = static_cast<int>(o->element_index_offset);
+  const int count_turns = (o->flags & XLB_OPT_NO_TURN_COUNT) ? 0 : 1;
 
   int occ = 1;
   XLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, threads, smem));
@@ -396,7 +417,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     a.n_blocks = static_cast<unsigned int>(blocks);
     a.n_items = static_cast<unsigned int>(blocks);
     a.turns_per_item = turns;
-    a.count_turns = 1;
+    a.count_turns = count_turns;
     if (split) {
       // turn by turn, segment by segment: tracking kernel up to the next 6D lens, the lens
       // kernel, and so on; the closing MAIN segment counts the turn
@@ -414,7 +435,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
           } else {
             a.lat = first;
             a.n_chunks = sg[1];
-            a.count_turns = (k == lat->n_segments - 1) ? 1 : 0;
+            a.count_turns = (k == lat->n_segments - 1) ? count_turns : 0;
             v->launch(a, blocks, threads, smem, st);
           }
           g_stats.kernel_launches += 1;
@@ -657,6 +678,16 @@ int xlb_compact_alive_device(const int64_t *state, int64_t n, int32_t *idx_out, 
   Scratch *s = nullptr;
   int rc = get_scratch(&s);
   if (rc != XLB_OK) return rc;
+  std::lock_guard<std::recursive_mutex> call_lock(s->call_mu);
+  cudaStream_t cst = static_cast<cudaStream_t>(stream);
+  if (s->have_done) XLB_CUDA(cudaStreamWaitEvent(cst, s->done, 0));
+  struct DoneMark {
+    Scratch *s;
+    cudaStream_t st;
+    ~DoneMark() {
+      if (cudaEventRecord(s->done, st) == cudaSuccess) s->have_done = true;
+    }
+  } done_mark{s, cst};
   if ((rc = ensure_compaction_scratch(s, 1)) != XLB_OK) return rc;
   const int nblocks = static_cast<int>((n + CP_THREADS * CP_ITEMS - 1) / (CP_THREADS * CP_ITEMS));
   if (nblocks > s->nblocks_cap) {
@@ -680,6 +711,7 @@ int xlb_track_host(const xlb_lattice_t *hl, xlb_particles_t *hp, const xlb_track
   if (n == 0 || o->num_turns == 0) return XLB_OK;
   Scratch *s = nullptr;
   if ((rc = get_scratch(&s)) != XLB_OK) return rc;
+  std::lock_guard<std::recursive_mutex> call_lock(s->call_mu);
   if (!s->stream) XLB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   cudaStream_t st = s->stream;
 

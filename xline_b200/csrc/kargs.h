@@ -32,6 +32,7 @@ struct KArgs {
   // added to the per-particle turn counter at every END_TURN: 1, except for the passes over
   // the leading segments of a segmented lattice (xlb_lattice_t::segments), where it is 0
   int count_turns;
+  int elem_off;  // added to the element index written to at_element (xlb_track_options_t)
   // element-by-element trace (debug kernels only): [n_elements][6][trace_n] fp64
   double *trace;
   long long trace_n;

@@ -11,12 +11,112 @@ like ``xline/base_classes.py:59-82``.
 """
 import copy as _copy
 
+import numpy as _np
+
 __all__ = [
     "Element", "Drift", "DriftExact", "Multipole", "RFMultipole", "Cavity", "SawtoothCavity",
     "XYShift", "SRotation", "LimitRect", "LimitEllipse", "LimitRectEllipse", "BeamMonitor",
     "DipoleEdge", "BeamBeam4D", "BeamBeam6D", "SCCoasting", "SCQGaussProfile",
-    "SCInterpolatedProfile", "element_classes",
+    "SCInterpolatedProfile", "Elens", "LimitPolygon", "element_classes",
 ]
+
+
+# ---- edit tracking ---------------------------------------------------------------------------
+# The reference reads element fields on every ``track`` call (xline/elements.py), so code written
+# against it edits fields in place -- ``el.voltage = ...``, ``el.knl[1] = ...``,
+# ``line.elements.append(...)`` -- and expects the next ``Line.track`` to see it.  Here the fields
+# are packed once into the device lattice, so every edit made *through an element* (attribute
+# assignment, item assignment / in-place arithmetic on a list- or array-valued field, mutation of
+# ``Line.elements``) advances a global edit clock and stamps the owner with it; ``Line.pack``
+# compares the clock (O(1) when nothing was edited anywhere) and re-packs when an element of the
+# line carries a newer stamp.  List and array values are COPIED into tracked containers on
+# assignment: the element owns its data, an edit of the caller's original object afterwards does
+# not reach the element (the reference would alias it).
+_EDIT_CLOCK = [0]
+
+
+def edit_clock():
+    return _EDIT_CLOCK[0]
+
+
+def _touch(owner):
+    _EDIT_CLOCK[0] += 1
+    if owner is not None:
+        object.__setattr__(owner, "_rev", _EDIT_CLOCK[0])
+
+
+def _mutator(name):
+    base = getattr(list, name)
+
+    def method(self, *a, **k):
+        out = base(self, *a, **k)
+        _touch(self._owner)
+        return out
+
+    method.__name__ = name
+    return method
+
+
+class _FieldList(list):
+    """``list`` that stamps its owner (an element or a line) on every mutation."""
+
+    __slots__ = ("_owner",)
+
+    def __init__(self, values=(), owner=None):
+        list.__init__(self, values)
+        self._owner = owner
+
+    for _n in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop",
+               "remove", "clear", "sort", "reverse"):
+        locals()[_n] = _mutator(_n)
+    del _n
+
+    def __deepcopy__(self, memo):
+        return [_copy.deepcopy(v, memo) for v in self]
+
+    def __copy__(self):
+        return list(self)
+
+    def __reduce_ex__(self, protocol):
+        return (list, (list(self),))
+
+
+class _FieldArray(_np.ndarray):
+    """``ndarray`` that stamps its owner on item assignment and in-place arithmetic."""
+
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+    def __setitem__(self, key, value):
+        _np.ndarray.__setitem__(self, key, value)
+        _touch(self._owner)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = lambda v: v.view(_np.ndarray) if isinstance(v, _FieldArray) else v  # noqa: E731
+        if out is not None:
+            for o in out:
+                if isinstance(o, _FieldArray):
+                    _touch(o._owner)
+            kwargs["out"] = tuple(plain(o) for o in out)
+        return getattr(ufunc, method)(*[plain(v) for v in inputs], **kwargs)
+
+    def __deepcopy__(self, memo):
+        return _np.array(self, copy=True).view(_np.ndarray)
+
+    def __reduce_ex__(self, protocol):
+        return _np.array(self).view(_np.ndarray).__reduce_ex__(protocol)
+
+
+def _tracked(value, owner):
+    if isinstance(value, _np.ndarray):
+        arr = _np.array(value, copy=True).view(_FieldArray)
+        arr._owner = owner
+        return arr
+    if isinstance(value, list):
+        return _FieldList(value, owner)
+    return value
 
 
 class Element:
@@ -26,7 +126,15 @@ class Element:
 
     _base = ()
     _extra = ()
+    _untracked = ("data",)  # BeamMonitor.data is an output, re-published after every track call
     iscollective = False  # xline/base_classes.py:57
+
+    def __setattr__(self, name, value):
+        if name.startswith("_") or name in self._untracked:
+            object.__setattr__(self, name, value)
+            return
+        object.__setattr__(self, name, _tracked(value, self))
+        _touch(self)
 
     def __init__(self, *args, **kwargs):
         names = [n for n, _ in self._base] + [n for n, _ in self._extra]
@@ -71,7 +179,14 @@ class Element:
         return self._names(keepextra)
 
     def to_dict(self, keepextra=False):
-        out = {k: getattr(self, k) for k in self._names(keepextra)}
+        out = {}
+        for k in self._names(keepextra):
+            v = getattr(self, k)
+            if isinstance(v, _FieldList):  # plain containers outward (copies: edits go through the element)
+                v = list(v)
+            elif isinstance(v, _FieldArray):
+                v = _np.array(v).view(_np.ndarray)
+            out[k] = v
         out["__class__"] = type(self).__name__
         return out
 
@@ -94,16 +209,34 @@ class Element:
         return "%s(%s)" % (type(self).__name__, body)
 
     def __eq__(self, other):
-        return type(other) is type(self) and self.to_dict(True) == other.to_dict(True)
+        if type(other) is not type(self):
+            return False
+        a, b = self.to_dict(True), other.to_dict(True)
+        if a.keys() != b.keys():
+            return False
+        for k, v in a.items():
+            w = b[k]
+            if isinstance(v, _np.ndarray) or isinstance(w, _np.ndarray):
+                if not _np.array_equal(_np.asarray(v), _np.asarray(w)):
+                    return False
+            elif v != w:
+                return False
+        return True
 
     __hash__ = None
 
     # -- the operator the reference defines on every element -------------------------
     def track(self, p):
-        """``el.track(p)``: push ``p`` through this single element on the GPU (in place)."""
+        """``el.track(p)``: push ``p`` through this single element on the GPU (in place).  Like the
+        reference's ``el.track`` it does not touch the turn counter (``at_turn`` advances in
+        ``Line.track`` only); the one-element lattice is cached on the element until it is edited."""
         from .line import Line
 
-        return Line(elements=[self], element_names=["e0"]).track(p)
+        solo = self.__dict__.get("_solo")
+        if solo is None or solo[0] != self.__dict__.get("_rev"):
+            solo = (self.__dict__.get("_rev"), Line(elements=[self], element_names=["e0"]))
+            object.__setattr__(self, "_solo", solo)
+        return solo[1].track(p, _count_turns=False)
 
 
 def _zero_list():
@@ -179,6 +312,24 @@ class LimitEllipse(Element):
     """Elliptical aperture (xline/elements.py:423-442)."""
 
     _base = (("a", 1.0), ("b", 1.0))
+
+
+class LimitPolygon(Element):
+    """Polygonal aperture (xline/elements.py:476-483).  The reference's ``track`` raises
+    ``NotImplementedError``; so does packing a line that contains one.  The class exists so that
+    the MAD-X ``octagon`` mapping (xline/loader_mad.py:229-242) and ``Line.from_dict`` work."""
+
+    _base = (("x_vertices", tuple), ("y_vertices", tuple))
+
+
+class Elens(Element):
+    """Hollow electron lens (xline/elements.py:281-370): parameters only.  Its map is outside the
+    hot path this package serves (SURVEY.md section 8a: debug prints in the reference's ``track``);
+    packing a line that contains one raises ``ValueError``.  The class exists so that
+    ``Line.from_dict`` reads the reference's JSON files."""
+
+    _base = (("voltage", 0), ("current", 0), ("inner_radius", 0), ("outer_radius", 0),
+             ("ebeam_center_x", 0), ("ebeam_center_y", 0), ("elens_length", 0))
 
 
 class LimitRectEllipse(Element):

@@ -26,6 +26,17 @@ def _is_thick(element):
 
 class Line(E.Element):
     _base = (("elements", tuple), ("element_names", tuple))
+    _pack_options = ("fuse_records", "chunk_words", "merge_multipoles", "split_lenses")
+
+    def __setattr__(self, name, value):
+        # edit tracking (elements.py): the element list and the packing options stamp the line,
+        # everything else (caches, outputs such as loss_tally / last_stats) is plain state
+        if name in ("elements", "element_names"):
+            E.Element.__setattr__(self, name, list(value))
+        else:
+            object.__setattr__(self, name, value)
+            if name in self._pack_options:
+                E._touch(self)
 
     def __init__(self, elements=(), element_names=None):
         self.elements = list(elements)
@@ -39,6 +50,7 @@ class Line(E.Element):
         self.merge_multipoles = True  # fast encoding: co-located thin multipoles become one kick
         self.split_lenses = True      # fast encoding: BeamBeam6D lenses run as kernels of their own
         self._monitor_buf = None
+        self._buffers_key = None
         self.loss_tally = None
         self.last_stats = None
 
@@ -88,9 +100,14 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ editing (host)
     def invalidate(self):
-        """Drop the packed-lattice cache (call after editing element fields in place)."""
+        """Drop the packed-lattice cache, the loss tallies and the monitor storage.  Edits made
+        through the elements or the line (``el.voltage = ...``, ``el.knl[1] = ...``,
+        ``line.elements.append(...)``) are noticed by ``pack`` on their own (edit tracking,
+        ``elements.py``); this call is for what tracking cannot see -- elements of foreign classes
+        (the reference's own, duck-typed) edited in place."""
         self._cache.clear()
         self._monitor_buf = None
+        self._buffers_key = None
         self.loss_tally = None
 
     def insert_element(self, idx, element, name):
@@ -249,12 +266,37 @@ class Line(E.Element):
     def algorithmic_ops_per_turn(self):
         return algorithmic_ops(self.elements)
 
+    def _content_stamp(self):
+        """(ids of the elements, newest edit stamp among them and the line): changes whenever the
+        element list or a tracked field changed.  O(len) -- only evaluated when the global edit
+        clock moved since the last look."""
+        newest = self.__dict__.get("_rev", 0)
+        for el in self.elements:
+            r = el.__dict__.get("_rev", 0) if hasattr(el, "__dict__") else 0
+            if r > newest:
+                newest = r
+        return (tuple(map(id, self.elements)), newest)
+
+    def _current_stamp(self):
+        clock = E.edit_clock()
+        seen = self._cache.get("stamp")
+        if seen is not None and seen[0] == clock and seen[2] == len(self.elements):
+            return seen[1]
+        stamp = self._content_stamp()
+        if seen is None or seen[1] != stamp:
+            self._cache.clear()  # the line changed: packed lattices and device copies are stale
+            self._cache["generation"] = Line._generations = getattr(Line, "_generations", 0) + 1
+        self._cache["stamp"] = (clock, stamp, len(self.elements))
+        return stamp
+
     def pack(self, strict=False, chunk_words=None):
-        """Host-side packed lattice (``lattice.PackedLattice``), cached."""
+        """Host-side packed lattice (``lattice.PackedLattice``), cached until the line or one of
+        its elements is edited."""
         if chunk_words is None:
             chunk_words = self.chunk_words
+        self._current_stamp()
         key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles, self.split_lenses,
-               getattr(self, "_keep_noops", False), tuple(map(id, self.elements)))
+               getattr(self, "_keep_noops", False))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -279,7 +321,8 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ the hot path
     def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
-              threads_per_block=0, timed=False, turns_per_item=0, _trace=None):
+              threads_per_block=0, timed=False, turns_per_item=0, _trace=None, _count_turns=True,
+              _element_offset=0):
         """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
         times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
         returns ``None`` like the reference.
@@ -292,8 +335,9 @@ class Line(E.Element):
                 "xline_b200.Line.track needs particles resident on a CUDA device (got %s); "
                 "there is no CPU tracking path in this package" % p.device)
         lib = _cabi.lib()
-        with torch.cuda.device(p.device):
-            packed, words = self._device_lattice(p.device, strict)
+        dev = p.x.device  # the tensors' own (indexed) device: torch.device("cuda") != torch.device("cuda:0")
+        with torch.cuda.device(dev):
+            packed, words = self._device_lattice(dev, strict)
             n = len(p)
             if n == 0 or num_turns == 0:
                 return None
@@ -310,8 +354,13 @@ class Line(E.Element):
                 setattr(cp, k, t.data_ptr())
             cp.q0, cp.mass0, cp.p0c = p.q0, p.mass0, p.p0c
             cp.beta0, cp.gamma0, cp.energy0 = p.beta0, p.gamma0, p.energy0
-            if self.loss_tally is None or self.loss_tally.device != p.device:
-                self.loss_tally = torch.zeros(max(packed.n_elements, 1), dtype=torch.int64, device=p.device)
+            # tallies and monitor storage belong to one state of the line on one device: a line that
+            # was edited since (other element count, other monitor layout) gets fresh ones
+            bkey = (self._cache.get("generation"), packed.n_elements, packed.monitor_words, dev)
+            if self._buffers_key != bkey or self.loss_tally is None:
+                self.loss_tally = torch.zeros(max(packed.n_elements, 1), dtype=torch.int64, device=dev)
+                self._monitor_buf = None
+                self._buffers_key = bkey
             if particles_per_thread == 0 and (packed.flags & 2) and not strict:
                 # beam-field lattice: the thin-lens records still dominate when lenses are
                 # sparse (LHC + 74 lenses: 3 particles/thread wins); dense space-charge
@@ -329,17 +378,19 @@ class Line(E.Element):
             opts.threads_per_block = int(threads_per_block)
             opts.turns_per_launch = int(turns_per_launch)
             opts.turns_per_item = int(turns_per_item)
+            opts.flags = 0 if _count_turns else _cabi.OPT_NO_TURN_COUNT
+            opts.element_index_offset = int(_element_offset)
             if _trace is not None:
                 opts.trace = _trace.data_ptr()
                 opts.trace_particles = int(_trace.shape[2])
             opts.loss_tally = self.loss_tally.data_ptr()
             if packed.monitor_words > 0:
-                if self._monitor_buf is None or self._monitor_buf.device != p.device:
+                if self._monitor_buf is None:
                     self._monitor_buf = torch.full((packed.monitor_words,), float("nan"),
-                                                   dtype=torch.float64, device=p.device)
+                                                   dtype=torch.float64, device=dev)
                 opts.monitor_data = self._monitor_buf.data_ptr()
                 opts.monitor_words = packed.monitor_words
-            stream = torch.cuda.current_stream(p.device).cuda_stream
+            stream = torch.cuda.current_stream(dev).cuda_stream
             fn = lib.xlb_track_device_timed if timed else lib.xlb_track_device
             _cabi.check(fn(C.byref(lat), C.byref(cp), C.byref(opts), C.c_void_p(stream)))
             self.last_stats = _cabi.stats()
@@ -369,28 +420,38 @@ class Line(E.Element):
         a particle was lost.  ``p`` is tracked in place.  The line is packed element by element
         (no record fusing, no merging, no-ops kept) so every element owns a row."""
         n = len(p)
-        k = n if max_particles is None else min(int(max_particles), n)
-        saved = (self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache)
-        self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache = False, False, False, {}
+        k_ = n if max_particles is None else min(int(max_particles), n)
+        # temporary packing options with a cache of their own; set without stamping the line, so the
+        # regular packed lattice stays valid afterwards
+        names = ("fuse_records", "merge_multipoles", "split_lenses", "_cache", "_buffers_key", "loss_tally",
+                 "_monitor_buf")
+        saved = {k: self.__dict__[k] for k in names}
+        for k, v in zip(names, (False, False, False, {}, None, None, None)):
+            object.__setattr__(self, k, v)
         self._keep_noops = True
         try:
-            trace = torch.full((len(self) + 1, 6, k), float("nan"), dtype=torch.float64, device=p.device)
+            trace = torch.full((len(self) + 1, 6, k_), float("nan"), dtype=torch.float64, device=p.device)
             for f, name in enumerate(("x", "px", "y", "py", "zeta", "delta")):
-                trace[0, f] = getattr(p, name)[:k]
+                trace[0, f] = getattr(p, name)[:k_]
             self.track(p, num_turns=1, strict=strict, _trace=trace[1:])
         finally:
             self._keep_noops = False
-            self.fuse_records, self.merge_multipoles, self.split_lenses, self._cache = saved
+            for k, v in saved.items():
+                object.__setattr__(self, k, v)
         return trace
 
     def track_elem_by_elem(self, p, start=True, end=False):
         """Debug path (xline/line.py:97-108): one single-element launch per element,
-        returning the copies of ``p`` the reference returns."""
+        returning the copies of ``p`` the reference returns.  As there, the turn counter is not
+        touched; a particle lost on the way records the index of the element in THIS line."""
         out = []
         if start:
             out.append(p.copy())
-        for el in self.elements:
-            Line([el], ["e"]).track(p)
+        for i, el in enumerate(self.elements):
+            solo = self._cache.get(("solo", i))
+            if solo is None or solo.elements[0] is not el:
+                solo = self._cache[("solo", i)] = Line([el], ["e"])
+            solo.track(p, _count_turns=False, _element_offset=i)
             out.append(p.copy())
         if end:
             out.append(p.copy())

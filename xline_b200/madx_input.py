@@ -50,6 +50,9 @@ _TYPE_DEFAULTS = {
     "kicker": dict(hkick=0.0, vkick=0.0), "tkicker": dict(hkick=0.0, vkick=0.0),
     "rfcavity": dict(volt=0.0, freq=0.0, lag=0.0),
     "dipedge": dict(h=0.0, e1=0.0, hgap=0.0, fint=0.0),
+    "rfmultipole": dict(volt=0.0, freq=0.0, lag=0.0, knl=[0.0], ksl=[0.0], pnl=[0.0], psl=[0.0]),
+    "crabcavity": dict(volt=0.0, freq=0.0, lag=0.0, tilt=0.0),
+    "beambeam": dict(slot_id=0),
 }
 
 
@@ -79,10 +82,13 @@ class MadElement:
 
 
 class MadSequence:
-    def __init__(self, name, length, elements):
+    def __init__(self, name, length, elements, beam=None):
         self.name = name
         self.length = length
         self.elements = elements
+        # the BEAM attached to the sequence (cpymad: ``sequence.beam``); the crab-cavity mapping
+        # reads ``beam.pc`` [GeV] (xline/loader_mad.py:108-125)
+        self.beam = beam
 
     def element_positions(self):
         return [e.position for e in self.elements]
@@ -109,7 +115,7 @@ _BASE_TYPES = {
     "quadrupole", "sbend", "rbend", "sextupole", "octupole", "marker", "monitor", "hmonitor",
     "vmonitor", "instrument", "drift", "hkicker", "vkicker", "kicker", "tkicker", "rfcavity",
     "multipole", "dipedge", "collimator", "rcollimator", "ecollimator", "elseparator", "solenoid",
-    "placeholder", "sequence",
+    "placeholder", "sequence", "rfmultipole", "crabcavity", "beambeam",
 }
 _STRING_ATTRS = {"apertype", "particle", "file", "flag", "style", "sequence", "pattern", "class", "range",
                  "refer", "refpos", "from", "format", "table", "column", "period", "type", "name"}
@@ -479,6 +485,18 @@ class MadxFile:
             entry = pos - {"entry": 0.0, "centre": 0.5 * length, "exit": length}[refer]
             out.append(MadElement(ename, base, attrs, offset + entry))
 
+    def _beam_namespace(self):
+        """``beam`` command attributes as cpymad exposes them; ``pc`` [GeV] is derived from ``energy``
+        and the particle mass when only the energy was given."""
+        b = dict(self.beam)
+        mass = b.get("mass", {"proton": 0.93827208816, "electron": 0.51099895e-3,
+                              "positron": 0.51099895e-3}.get(str(b.get("particle", "proton")).lower()))
+        if "pc" not in b and "energy" in b and mass is not None:
+            b["pc"] = math.sqrt(max(float(b["energy"]) ** 2 - mass ** 2, 0.0))
+        if "energy" not in b and "pc" in b and mass is not None:
+            b["energy"] = math.hypot(float(b["pc"]), mass)
+        return SimpleNamespace(**b)
+
     def _thick_sequence(self, name, markers=False):
         """The flattened thick sequence: elements at their ENTRY positions."""
         out = []
@@ -487,7 +505,7 @@ class MadxFile:
         if markers:
             out = ([MadElement(name + "$start", "marker", {}, 0.0)] + out
                    + [MadElement(name + "$end", "marker", {}, length)])
-        return MadSequence(name, length, out)
+        return MadSequence(name, length, out, self._beam_namespace())
 
     def _plain_used(self, name):
         if name not in self._thin:
@@ -516,7 +534,7 @@ class MadxFile:
                 dkn[:len(rec.get("dkn", []))] = rec.get("dkn", [])
                 dks[:len(rec.get("dks", []))] = rec.get("dks", [])
                 el.field_errors = SimpleNamespace(dkn=dkn, dks=dks)
-        return MadSequence(name, base.length, els)
+        return MadSequence(name, base.length, els, base.beam)
 
 
 def _split_top(text):
@@ -644,7 +662,7 @@ def makethin(seq, slices=None, default_slices=1, slice_fn=None, centre_markers=F
         else:
             out.append(MadElement(el.name, base, el.attributes(), el.position))
     out.sort(key=lambda e: e.position)
-    return MadSequence(seq.name, seq.length, out)
+    return MadSequence(seq.name, seq.length, out, getattr(seq, "beam", None))
 
 
 _DRIFT_LIKE = ("marker", "monitor", "hmonitor", "vmonitor", "collimator", "rcollimator", "elseparator",
@@ -670,11 +688,15 @@ def iter_from_madx_sequence(sequence, classes, ignored_madtypes=(), exact_drift=
             i_drift += 1
         kind = ee.base_type.name
         new = None
+        skiptilt = False
         if kind in _DRIFT_LIKE:
             new = Drift(length=ee.l)
             old_pp += ee.l
         elif kind in ignored_madtypes:
-            pass
+            # the reference falls through with whatever `newele` held before (loader_mad.py:55-56:
+            # the previous element again, or a NameError for the first one); an ignored type is
+            # skipped here
+            continue
         elif kind == "multipole":
             knl = list(getattr(ee, "knl", [0]))
             ksl = list(getattr(ee, "ksl", [0]))
@@ -690,6 +712,30 @@ def iter_from_madx_sequence(sequence, classes, ignored_madtypes=(), exact_drift=
             new = classes["DipoleEdge"](h=ee.h, e1=ee.e1, hgap=ee.hgap, fint=ee.fint)
         elif kind == "rfcavity":
             new = classes["Cavity"](voltage=ee.volt * 1e6, frequency=ee.freq * 1e6, lag=ee.lag * 360)
+        elif kind == "rfmultipole":  # loader_mad.py:97-106
+            new = classes["RFMultipole"](voltage=ee.volt * 1e6, frequency=ee.freq * 1e6, lag=ee.lag * 360,
+                                         knl=list(ee.knl), ksl=list(ee.ksl), pn=[v * 360 for v in ee.pnl],
+                                         ps=[v * 360 for v in ee.psl])
+        elif kind == "crabcavity":  # loader_mad.py:108-125: ee.volt in MV, sequence.beam.pc in GeV
+            pc = sequence.beam.pc
+            if abs(ee.tilt - math.pi / 2) < 1e-9:
+                new = classes["RFMultipole"](frequency=ee.freq * 1e6, ksl=[-ee.volt / pc * 1e-3],
+                                             ps=[ee.lag * 360 + 90])
+                skiptilt = True
+            else:
+                new = classes["RFMultipole"](frequency=ee.freq * 1e6, knl=[ee.volt / pc * 1e-3],
+                                             pn=[ee.lag * 360 + 90])
+        elif kind == "beambeam":  # loader_mad.py:128-170: placeholders, to be configured afterwards
+            if int(getattr(ee, "slot_id", 0)) in (6, 60):
+                new = classes["BeamBeam6D"](
+                    phi=0.0, alpha=0.0, x_bb_co=0.0, y_bb_co=0.0, charge_slices=[0.0], zeta_slices=[0.0],
+                    sigma_11=1.0, sigma_12=0.0, sigma_13=0.0, sigma_14=0.0, sigma_22=1.0, sigma_23=0.0,
+                    sigma_24=0.0, sigma_33=0.0, sigma_34=0.0, sigma_44=0.0, x_co=0.0, px_co=0.0, y_co=0.0,
+                    py_co=0.0, zeta_co=0.0, delta_co=0.0, d_x=0.0, d_px=0.0, d_y=0.0, d_py=0.0, d_zeta=0.0,
+                    d_delta=0.0)
+            else:
+                new = classes["BeamBeam4D"](charge=0.0, sigma_x=1.0, sigma_y=1.0, beta_r=1.0, x_bb=0.0,
+                                            y_bb=0.0, d_px=0.0, d_py=0.0)
         elif kind == "placeholder":
             slot = int(getattr(ee, "slot_id", 0))
             if slot in (1, 2, 3):
@@ -699,7 +745,7 @@ def iter_from_madx_sequence(sequence, classes, ignored_madtypes=(), exact_drift=
                 old_pp += ee.l
         else:
             raise ValueError('MAD element "%s" not recognized' % kind)
-        tilt = math.degrees(ee.tilt) if abs(getattr(ee, "tilt", 0.0)) > 0 else 0
+        tilt = math.degrees(ee.tilt) if (abs(getattr(ee, "tilt", 0.0)) > 0 and not skiptilt) else 0
         if abs(tilt) > 0:
             yield ee.name + "_pretilt", classes["SRotation"](angle=tilt)
         yield ee.name, new
@@ -715,6 +761,12 @@ def iter_from_madx_sequence(sequence, classes, ignored_madtypes=(), exact_drift=
                 yield ee.name + "_aperture", classes["LimitEllipse"](a=ap[0], b=ap[0])
             elif ee.apertype == "rectellipse":
                 yield ee.name + "_aperture", classes["LimitRectEllipse"](max_x=ap[0], max_y=ap[1], a=ap[2], b=ap[3])
+            elif ee.apertype == "octagon":  # loader_mad.py:229-242 (LimitPolygon: tracking raises, as there)
+                v1 = (ap[0], ap[0] * math.tan(ap[2]))
+                v2 = (ap[1] / math.tan(ap[3]), ap[1])
+                yield ee.name + "_aperture", classes["LimitPolygon"](
+                    x_vertices=[v1[0], v2[0], -v2[0], -v1[0], -v1[0], -v2[0], v2[0], v1[0]],
+                    y_vertices=[v1[1], v2[1], v2[1], v1[1], -v1[1], -v2[1], -v2[1], -v1[1]])
             else:
                 raise ValueError("Aperture type not recognized")
     if sequence.length > old_pp:
