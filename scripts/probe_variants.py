@@ -27,6 +27,7 @@ def child(libname, cfgs):
              "c4r": (configs.config_petra4, 1_000_000, 40), "c5": (configs.config_psb, 1_000_000, 200)}
     for c in cfgs:
         fn, n, turns = table[c]
+        n = int(os.environ.get("XLB_PROBE_N", n))  # particles (default: 1 M)
         line, cols, p0c, m0 = fn(n)
         # XLB_PROBE_SHAPES="3x128,2x256": particles per thread x threads per block (default: library's choice)
         for shape in os.environ.get("XLB_PROBE_SHAPES", "0x0").split(","):

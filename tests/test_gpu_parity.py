@@ -901,6 +901,9 @@ def test_edited_line_gets_fresh_buffers_and_repacks():
     """(a) a line that grew since the last call must not keep its old, smaller loss
     tally; (b) torch.device("cuda") vs "cuda:0" must not reset the tallies on every call; (c) a
     field edited in place (the reference reads fields on every track call) must be tracked through."""
+    import xline_b200 as xl
+    from xline_b200 import configs
+
     n = 2000
     base, cols, p0c, m0 = configs.config_fodo(n)
     line = xl.Line(list(base.elements) + [xl.LimitRect(min_x=-2e-3, max_x=2e-3, min_y=-2e-3, max_y=2e-3)])
@@ -946,6 +949,9 @@ def test_element_track_loop_is_one_pass_of_the_line():
     """`for el in line.elements: el.track(p)` (the reference's loop, xline/line.py:89-95) equals
     Line.track(p) without touching the turn counter; track_elem_by_elem records the index of the
     element in the line for a particle lost on the way."""
+    import xline_b200 as xl
+    from xline_b200 import configs
+
     n = 600
     base, cols, p0c, m0 = configs.config_fodo(n)
     els = list(base.elements) + [xl.LimitRect(min_x=-1.5e-3, max_x=1.5e-3, min_y=-1.5e-3, max_y=1.5e-3)]

@@ -157,7 +157,21 @@ struct Scratch {
   std::recursive_mutex call_mu;
   cudaEvent_t done = nullptr;
   bool have_done = false;
+  // launch-length schedule (see track_device_impl): loss rate per turn seen by the last
+  // segmented call, and the particle set it belonged to
+  const double *sched_x = nullptr;
+  long long sched_n = 0;
+  double sched_rate = -1.0;
 };
+
+// Launch length for a loss rate: lanes of lost particles idle until the next launch boundary,
+// on average rate * length / 2 of the lanes over a launch -- keep that near 3 %.
+static int launch_length_for_rate(double rate_per_turn, int longest) {
+  if (!(rate_per_turn > 0)) return longest;
+  const double len = 0.06 / rate_per_turn;
+  if (len >= longest) return longest;
+  return len < 1.0 ? 1 : static_cast<int>(len);
+}
 static std::mutex g_mu;
 static std::vector<Scratch *> g_scratch;
 
@@ -388,6 +402,20 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   long long lost_since_compact = 0;
   const bool segmented = seg < o->num_turns;
   if (segmented) XLB_CUDA(cudaMemsetAsync(s->n_lost, 0, sizeof(unsigned int), st));
+  // Launch-length ramp: a beam that is scraped hard in its first turns (80 % of the
+  // C2 beam within a few turns) would keep those lanes idle for a whole launch.  A segmented job
+  // on a particle set not seen before starts with a launch of ONE turn; after every launch the
+  // loss rate per turn just measured sets the next length (at most twice the previous one, at
+  // most `seg`), and survivors are re-compacted as before.  A call that continues with the
+  // particle set of the previous call starts from the rate that call ended with.  The schedule
+  // never changes results (a launch boundary is invisible to the particles).
+  const bool ramp = segmented && p->n >= 32768;
+  int cur_len = seg;
+  if (ramp) {
+    const bool continuing = (s->sched_x == p->x && s->sched_n == p->n && s->sched_rate >= 0.0);
+    cur_len = continuing ? launch_length_for_rate(s->sched_rate, seg) : 1;
+  }
+  double last_rate = -1.0;
 
   if (timed) XLB_CUDA(cudaEventRecord(s->ev0, st));
   if (o->turns_per_launch > 0 || seg < o->num_turns) {
@@ -405,8 +433,9 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     }
   }
   float total_ms = 0.f;
+  long long lost_before_launch = 0;
   for (int done = 0; done < o->num_turns && n_active > 0;) {
-    const int turns = std::min(seg, o->num_turns - done);
+    const int turns = std::min(ramp ? cur_len : seg, o->num_turns - done);
     a.num_turns = turns;
     a.n = n_active;
     a.idx = idx;
@@ -470,6 +499,12 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
                              cudaMemcpyDeviceToHost, st));
     XLB_CUDA(cudaStreamSynchronize(st));
     const long long lost_total = s->h_pinned[0];
+    if (ramp) {
+      last_rate = static_cast<double>(lost_total - lost_before_launch) /
+                  (static_cast<double>(n_active) * static_cast<double>(turns));
+      cur_len = std::min(launch_length_for_rate(last_rate, seg), 2 * cur_len);
+    }
+    lost_before_launch = lost_total;
     const long long newly = lost_total - lost_since_compact;
     if (newly > 0 && static_cast<double>(newly) >= thr * static_cast<double>(n_active)) {
       if ((rc = ensure_compaction_scratch(s, p->n)) != XLB_OK) return rc;
@@ -487,6 +522,12 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     XLB_CUDA(cudaEventRecord(s->ev1, st));
     XLB_CUDA(cudaEventSynchronize(s->ev1));
     XLB_CUDA(cudaEventElapsedTime(&total_ms, s->ev0, s->ev1));
+  }
+  if (ramp) {
+    s->sched_x = p->x;
+    s->sched_n = p->n;
+    if (last_rate >= 0.0) s->sched_rate = last_rate;
+    else if (!(s->sched_rate >= 0.0)) s->sched_rate = 0.0;
   }
   g_stats.kernel_ms = total_ms;
   g_stats.regs_per_thread = fa.numRegs;

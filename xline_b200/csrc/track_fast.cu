@@ -51,13 +51,23 @@ void fast_bb6d_launch(const KArgs &a, const unsigned long long *rec, int blocks,
 }
 #endif
 #else
+// resident CTAs per SM the launch bounds ask for (experiment builds override them)
+#ifndef XLB_MINB_2_128
+#define XLB_MINB_2_128 3
+#endif
+#ifndef XLB_MINB_3_128
+#define XLB_MINB_3_128 3
+#endif
 XLB_DEF_VARIANT(1, 128, 5)
 XLB_DEF_VARIANT(1, 256, 3)
 XLB_DEF_VARIANT(1, 512, 2)
-XLB_DEF_VARIANT(2, 128, 3)
+XLB_DEF_VARIANT(2, 128, XLB_MINB_2_128)
 XLB_DEF_VARIANT(2, 256, 2)
-XLB_DEF_VARIANT(3, 128, 3)
+XLB_DEF_VARIANT(3, 128, XLB_MINB_3_128)
 XLB_DEF_VARIANT(4, 128, 2)
+#if XLB_EXP_T160
+XLB_DEF_VARIANT(3, 160, 3)
+#endif
 
 #if XLB_BEAMFIELDS
 #define XLB_TABLE fast_bf_table
@@ -72,10 +82,13 @@ static const Variant XLB_TABLE[] = {
     XLB_VARIANT_ENTRY("fast/ppt1/t128" XLB_SUFFIX, 1, 128, 5),
     XLB_VARIANT_ENTRY("fast/ppt1/t256" XLB_SUFFIX, 1, 256, 3),
     XLB_VARIANT_ENTRY("fast/ppt1/t512" XLB_SUFFIX, 1, 512, 2),
-    XLB_VARIANT_ENTRY("fast/ppt2/t128" XLB_SUFFIX, 2, 128, 3),
+    XLB_VARIANT_ENTRY("fast/ppt2/t128" XLB_SUFFIX, 2, 128, XLB_MINB_2_128),
     XLB_VARIANT_ENTRY("fast/ppt2/t256" XLB_SUFFIX, 2, 256, 2),
-    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, 3),
+    XLB_VARIANT_ENTRY("fast/ppt3/t128" XLB_SUFFIX, 3, 128, XLB_MINB_3_128),
     XLB_VARIANT_ENTRY("fast/ppt4/t128" XLB_SUFFIX, 4, 128, 2),
+#if XLB_EXP_T160
+    XLB_VARIANT_ENTRY("fast/ppt3/t160" XLB_SUFFIX, 3, 160, 3),
+#endif
     XLB_TRACE_ENTRY("fast/trace"),
 };
 const Variant *XLB_TABLE_FN(int *n) {
