@@ -139,10 +139,16 @@ typedef struct xlb_lattice {
 #define XLB_F_BB6D 4u        /* lattice contains BEAMBEAM6D records: in MAIN groups (then
                                 BEAMFIELDS is set too and the kernels that carry the 6D
                                 lens are used) or in XLB_SEG_BB6D groups                */
+#define XLB_F_LOW_ORDER 8u   /* every MULTIPOLE / block record has order (aux) <= 3: the
+                                kernels with a straight-line Horner evaluation may be used
+                                (checked by xlb_lattice_validate; optional, never required) */
 
 /* Particle set, mirrors the attributes the reference's elements read and write
  * (SURVEY.md §8a row a2).  All arrays have length n.  chi and charge_ratio may be NULL
- * (treated as 1.0).  s, particle_id, at_element, at_turn may NOT be NULL. */
+ * (treated as 1.0).  chi == NULL is the fast case: one species, the reference's default -- the
+ * kernels compiled without a chi register are used (4 particles per thread instead of 3);
+ * xlb_track_host passes NULL on by itself when the host chi column is all ones.
+ * s, particle_id, at_element, at_turn may NOT be NULL. */
 typedef struct xlb_particles {
   int64_t n;
   double *x, *px, *y, *py, *zeta, *delta, *rpp, *rvv, *s;
@@ -154,10 +160,12 @@ typedef struct xlb_particles {
 
 typedef struct xlb_track_options {
   int32_t num_turns;         /* >= 0                                                     */
-  int32_t particles_per_thread; /* 0 = default (3; 2 for strict / beam-field lattices);
-                                   1..4                                                    */
-  int32_t threads_per_block;    /* 0 = default (128 at 3 particles/thread, else 256);
-                                   multiple of 32, <= the variant's launch bound           */
+  int32_t particles_per_thread; /* 0 = default (4 for thin-lens lattices with chi == NULL, 3
+                                   with a chi column or strict, 2 for beam-field lattices;
+                                   fewer when the beam would not fill the GPU); 1..4       */
+  int32_t threads_per_block;    /* 0 = default (128; 256 for beam-field lattices at 1-2
+                                   particles/thread); multiple of 32, <= the variant's
+                                   launch bound                                            */
   int32_t turns_per_launch;  /* > 0: survivors are re-compacted (warp-ballot stream
                                 compaction) between launches of this many turns; 0 =
                                 automatic (one launch up to 150 turns, else launches of 100

@@ -372,6 +372,37 @@ def test_kernel_variants_agree_bitwise(config):
             assert np.array_equal(ref[k], cur[k], equal_nan=True), (k, ppt, thr)
 
 
+@pytest.mark.parametrize("config", ["lhc", "petra4", "lhc_beambeam"])
+def test_kernel_families_agree_bitwise(config):
+    """The specialised kernel families (chi == 1 throughout: no chi register, 4 particles per
+    thread; multipole order <= 3: straight-line Horner) give the bits of the general kernels:
+    fma(-1, a, b) == b - a, and the Horner steps are the same operations in the same order."""
+    from xline_b200 import configs
+
+    n = 50_000
+    fn = {"lhc": configs.config_lhc, "petra4": configs.config_petra4, "lhc_beambeam": configs.config_lhc_beambeam}[config]
+    line, cols, p0c, m0 = fn(n)
+    packed = line.pack(False)
+    assert bool(packed.flags & 8) == (config != "lhc")  # XLB_F_LOW_ORDER
+    ref = make_particles(cols, p0c, m0)
+    line.track(ref, num_turns=2, particles_per_thread=3, threads_per_block=128, _general_kernels=True)
+    ref = ref.to_numpy()
+    names = set()
+    for ppt in (1, 2, 3, 4, 0):
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=2, particles_per_thread=ppt)
+        cur = p.to_numpy()
+        for k in ref:
+            assert np.array_equal(ref[k], cur[k], equal_nan=True), (k, ppt)
+    # a chi column that is not all ones goes through the general family and scales the kicks
+    p = make_particles(cols, p0c, m0)
+    p.chi[::2] = 1.0 + 1e-3
+    line.track(p, num_turns=1)
+    q = make_particles(cols, p0c, m0)
+    line.track(q, num_turns=1)
+    assert not torch.equal(p.px[::2], q.px[::2]) and torch.equal(p.px[1::2], q.px[1::2])
+
+
 def test_track_refuses_cpu_particles():
     import xline_b200 as xl
 

@@ -23,8 +23,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = [
     ("cabi", "cabi.cu", []),
     ("track_fast", "track_fast.cu", []),
+    ("track_fast_nc", "track_fast.cu", ["-DXLB_NOCHI=1"]),                      # chi == 1 throughout
+    ("track_fast_nc_lo", "track_fast.cu", ["-DXLB_NOCHI=1", "-DXLB_MAXORDER=3"]),  # + multipole order <= 3
     ("track_strict", "track_strict.cu", ["-fmad=false"]),
     ("track_fast_bf", "track_fast.cu", ["-DXLB_BEAMFIELDS=1"]),        # + BeamBeam4D, space charge
+    ("track_fast_bf_nc_lo", "track_fast.cu", ["-DXLB_BEAMFIELDS=1", "-DXLB_NOCHI=1", "-DXLB_MAXORDER=3"]),
     ("track_fast_bf6", "track_fast.cu", ["-DXLB_BEAMFIELDS=2"]),       # + BeamBeam6D
     ("track_strict_bf", "track_strict.cu", ["-DXLB_BEAMFIELDS=2", "-fmad=false"]),
 ]

@@ -15,9 +15,6 @@
 #include "kargs.h"
 
 namespace xlb {
-const Variant *fast_bf_variants(int *n);
-const Variant *fast_bf6_variants(int *n);
-const Variant *strict_bf_variants(int *n);
 
 static thread_local std::string g_err;
 static thread_local xlb_track_stats_t g_stats;
@@ -241,33 +238,58 @@ static int compact_alive(const long long *state, long long n, int *idx_out, int 
 }
 
 // ------------------------------------------------------------------ variant selection
-// Among the variants of the requested particles-per-thread, the one with the smallest
-// launch-bounds ceiling that still admits `threads` (tighter ceilings allow more registers).
-static const Variant *pick_variant(bool strict, bool beamfields, bool bb6d, int ppt, int threads,
-                                   bool trace) {
-  int n = 0;
-  const Variant *tab;
-  if (strict)
-    tab = beamfields ? strict_bf_variants(&n) : strict_variants(&n);
-  else
-    tab = beamfields ? (bb6d ? fast_bf6_variants(&n) : fast_bf_variants(&n)) : fast_variants(&n);
-  const Variant *best = nullptr;
-  for (int i = 0; i < n; ++i) {
-    const Variant &v = tab[i];
-    if (trace) {
-      if (v.trace) return &v;
-      continue;
+// All kernel families (one variant table per translation unit), most specialised first.
+typedef const Variant *(*TableFn)(int *);
+static const TableFn kTables[] = {fast_lean_nc_lo_variants, fast_lean_nc_variants, fast_lean_variants,
+                                  fast_bf_nc_lo_variants,   fast_bf_variants,      fast_bf6_variants,
+                                  strict_variants,          strict_bf_variants};
+static const int kNumTables = static_cast<int>(sizeof(kTables) / sizeof(kTables[0]));
+
+// What a call asks of a kernel family.
+struct Need {
+  bool strict, beamfields, bb6d, chi, trace;
+  int max_order;  // highest multipole order the lattice may hold (255 = unknown)
+};
+static bool admits(const Variant &v, const Need &q) {
+  if ((v.strict != 0) != q.strict) return false;
+  if (q.strict) return (v.beamfields != 0) == q.beamfields;
+  const int bf = q.beamfields ? (q.bb6d ? 2 : 1) : 0;
+  if (v.beamfields != bf) return false;
+  if (v.nochi && q.chi) return false;
+  if (v.maxorder && q.max_order > v.maxorder) return false;
+  return true;
+}
+// The first (most specialised) admissible family that has the requested particles-per-thread;
+// failing that, the closest particles-per-thread of the most specialised admissible family.
+// Within a family: the variant with the smallest launch-bounds ceiling that still admits
+// `threads` (tighter ceilings allow more registers).
+static const Variant *pick_variant(const Need &q, int ppt, int threads) {
+  const Variant *fallback = nullptr;
+  for (int t = 0; t < kNumTables; ++t) {
+    int n = 0;
+    const Variant *tab = kTables[t](&n);
+    const Variant *best = nullptr;
+    for (int i = 0; i < n; ++i) {
+      const Variant &v = tab[i];
+      if (!admits(v, q)) continue;
+      if (q.trace) {
+        if (v.trace) return &v;
+        continue;
+      }
+      if (v.trace) continue;
+      if (!best) { best = &v; continue; }
+      const int dv = std::abs(v.ppt - ppt), db = std::abs(best->ppt - ppt);
+      if (dv < db) { best = &v; continue; }
+      if (dv > db) continue;
+      const bool vfit = v.threads >= threads, bfit = best->threads >= threads;
+      if (vfit && (!bfit || v.threads < best->threads)) best = &v;
+      if (!vfit && !bfit && v.threads > best->threads) best = &v;
     }
-    if (v.trace) continue;
-    if (!best) { best = &v; continue; }
-    const int dv = std::abs(v.ppt - ppt), db = std::abs(best->ppt - ppt);
-    if (dv < db) { best = &v; continue; }
-    if (dv > db) continue;
-    const bool vfit = v.threads >= threads, bfit = best->threads >= threads;
-    if (vfit && (!bfit || v.threads < best->threads)) best = &v;
-    if (!vfit && !bfit && v.threads > best->threads) best = &v;
+    if (!best) continue;
+    if (best->ppt == ppt && best->threads >= threads) return best;
+    if (!fallback) fallback = best;
   }
-  return best;
+  return fallback;
 }
 
 static int check_lattice_header(const xlb_lattice_t *lat) {
@@ -327,18 +349,40 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const bool beamfields = (lat->flags & XLB_F_BEAMFIELDS) != 0;
   const bool split = lat->n_segments > 1;  // 6D lenses run as kernels of their own
   const bool bb6d = (lat->flags & XLB_F_BB6D) != 0 && !split;
-  // defaults from the B200 sweeps (scripts/probe_bench_sweep.py, scripts/probe_strict.py):
-  // thin-lens lattices run best with 3 particles per thread in 128-thread CTAs (3 CTAs/SM,
-  // 162 / 164 registers fast / strict, no spills); strict C2: 1.08e7 particle-turns/s against
-  // 9.1e6 (2 x 128), 7.3e6 (1 x 256), 6.7e6 (2 x 256)
-  const int ppt_req = o->particles_per_thread > 0 ? o->particles_per_thread : (beamfields ? 2 : 3);
-  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (ppt_req == 3 ? 128 : 256);
-  const bool trace = o->trace != nullptr;
+  // Defaults from the B200 sweeps (scripts/probe_variants.py, scripts/probe_strict.py).  Thin-lens
+  // lattices of one species (chi == NULL): 4 particles per thread in 128-thread CTAs, 3 CTAs/SM at
+  // 168 registers = 1 536 particles in flight per SM (C2 +5 %, C4 +23 % over 3 x 128 x 3); with a
+  // chi column 3 x 128 (162 registers, no spills).  Strict C2: 1.08e7 particle-turns/s with 3 x 128
+  // against 9.1e6 (2 x 128), 7.3e6 (1 x 256), 6.7e6 (2 x 256).  Beam-field lattices: 2 x 256 unless
+  // the caller knows the lenses are sparse (xline_b200/line.py decides from the record counts).
+  Need need;
+  need.strict = strict;
+  need.beamfields = beamfields;
+  need.bb6d = bb6d;
+  need.chi = p->chi != nullptr;
+  need.trace = o->trace != nullptr;
+  need.max_order = (lat->flags & XLB_F_LOW_ORDER) ? 3 : 255;
+  int ppt_req = o->particles_per_thread;
+  if (ppt_req <= 0) {
+    if (beamfields) ppt_req = 2;
+    else if (strict || need.chi) ppt_req = 3;
+    else ppt_req = 4;
+    // a small beam is spread over all SMs first: fewer particles per thread while the CTAs of the
+    // preferred shape would leave SMs without work (strong scaling, C1)
+    if (!beamfields && o->threads_per_block <= 0) {
+      int dev0 = 0, sms0 = 148;
+      cudaGetDevice(&dev0);
+      cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+      while (ppt_req > 1 && p->n < static_cast<long long>(ppt_req) * 128 * 3 * sms0) --ppt_req;
+    }
+  }
+  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (beamfields && ppt_req < 3 ? 256 : 128);
+  const bool trace = need.trace;
   if (trace && (o->num_turns != 1 || o->trace_particles < 1))
     return fail(XLB_EINVAL, "element-by-element trace needs num_turns == 1 and trace_particles >= 1");
   if (split && (trace || strict))
     return fail(XLB_EINVAL, "segmented lattices are for the fast kernels without trace");
-  const Variant *v = pick_variant(strict, beamfields, bb6d, ppt_req, threads_req, trace);
+  const Variant *v = pick_variant(need, ppt_req, threads_req);
   if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
   int threads = trace ? v->threads
                       : (o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req));
@@ -394,8 +438,10 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   const int tpi = (o->turns_per_item == 0) ? 5 : o->turns_per_item;
   // 0 = automatic: long jobs are cut into launches of 100 turns so that survivors get
   // re-compacted now and then; < 0 = one launch whatever the length
-  const int seg = (o->turns_per_launch > 0) ? o->turns_per_launch
-                  : (o->turns_per_launch == 0 && o->num_turns > 150 ? 100 : o->num_turns);
+  // (the kernel counts the chunks of a launch in 32 bits: a launch never exceeds 2^31 / n_chunks turns)
+  const int seg_cap = std::max(1, static_cast<int>(0x7fffffffLL / std::max(1, lat->n_chunks)));
+  const int seg = std::min(seg_cap, (o->turns_per_launch > 0) ? o->turns_per_launch
+                  : (o->turns_per_launch == 0 && o->num_turns > 150 ? 100 : o->num_turns));
   const double thr = (o->compact_threshold > 0) ? o->compact_threshold : (1.0 / 128.0);
   long long n_active = p->n;
   const int *idx = nullptr;
@@ -634,8 +680,12 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           break;
         case XLB_T_DRIFT:
         case XLB_T_DRIFT_EXACT: want = 1; break;
-        case XLB_T_MULTIPOLE: want = 1 + aux + 1; break;
-        case XLB_T_MULTIPOLE_CURVED: want = 3 + aux + 1; break;
+        case XLB_T_MULTIPOLE:
+        case XLB_T_MULTIPOLE_CURVED:
+          want = (tag == XLB_T_MULTIPOLE ? 1 : 3) + aux + 1;
+          if ((lat->flags & XLB_F_LOW_ORDER) && aux > 3)
+            return fail(XLB_ELATTICE, "XLB_F_LOW_ORDER set but a multipole has order > 3");
+          break;
         case XLB_T_CAVITY:
         case XLB_T_SAWTOOTH_CAVITY:
         case XLB_T_XYSHIFT:
@@ -667,6 +717,8 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
             want = 2;
             break;
           }
+          if ((tag & 0xc0) == XLB_T_THIN_BLOCK && (lat->flags & XLB_F_LOW_ORDER) && aux > 3)
+            return fail(XLB_ELATTICE, "XLB_F_LOW_ORDER set but a block record has order > 3");
           if ((tag & 0xe0) == XLB_T_THIN_BLOCK) {
             want = 2 + aux + 1 + ((tag & 4) ? 2 : 0) + ((tag & 3) ? 2 : 0);
             break;
@@ -783,7 +835,14 @@ int xlb_track_host(const xlb_lattice_t *hl, xlb_particles_t *hp, const xlb_track
     *dcols[c] = reinterpret_cast<double *>(take(col));
     XLB_CUDA(cudaMemcpyAsync(*dcols[c], hcols[c], static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
   }
-  if (hp->chi) {
+  // a chi column of ones is the one-species case: not uploaded, and the kernels without a chi
+  // register serve the call (see xlb_particles_t)
+  bool chi_trivial = true;
+  if (hp->chi)
+    for (long long i = 0; i < n; ++i)
+      if (hp->chi[i] != 1.0) { chi_trivial = false; break; }
+  if (chi_trivial) dp.chi = nullptr;
+  if (hp->chi && !chi_trivial) {
     double *d = reinterpret_cast<double *>(take(col));
     XLB_CUDA(cudaMemcpyAsync(d, hp->chi, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, st));
     dp.chi = d;
@@ -909,22 +968,21 @@ int xlb_selftest_exact_division(const double *divisors, int n_divisors, int mode
 }
 
 int xlb_kernel_variant_count(void) {
-  int a = 0, b = 0, c = 0, d = 0, e = 0;
-  fast_variants(&a);
-  strict_variants(&b);
-  fast_bf_variants(&c);
-  strict_bf_variants(&d);
-  fast_bf6_variants(&e);
-  return a + b + c + d + e;
+  int total = 0;
+  for (int t = 0; t < kNumTables; ++t) {
+    int n = 0;
+    kTables[t](&n);
+    total += n;
+  }
+  return total;
 }
 
 int xlb_kernel_variant_info(int i, char *name, int name_len, int *regs, int *max_threads) {
-  int n[5];
-  const Variant *t[5] = {fast_variants(&n[0]), strict_variants(&n[1]), fast_bf_variants(&n[2]),
-                         strict_bf_variants(&n[3]), fast_bf6_variants(&n[4])};
-  for (int k = 0; k < 5; ++k) {
-    if (i < n[k]) {
-      const Variant &v = t[k][i];
+  for (int t = 0; t < kNumTables; ++t) {
+    int n = 0;
+    const Variant *tab = kTables[t](&n);
+    if (i < n) {
+      const Variant &v = tab[i];
       if (name && name_len > 0) {
         strncpy(name, v.name, name_len - 1);
         name[name_len - 1] = 0;
@@ -936,7 +994,7 @@ int xlb_kernel_variant_info(int i, char *name, int name_len, int *regs, int *max
       if (e != cudaSuccess) cudaGetLastError();
       return XLB_OK;
     }
-    i -= n[k];
+    i -= n;
   }
   return fail(XLB_EINVAL, "variant index out of range");
 }

@@ -41,6 +41,8 @@ struct KArgs {
 struct Variant {
   const char *name;
   int strict, beamfields, ppt, threads, trace;
+  int nochi;     // 1 = compiled for chi == 1 throughout (xlb_particles_t::chi == NULL)
+  int maxorder;  // 0 = any multipole order; else the highest order the kernel evaluates (XLB_F_LOW_ORDER)
   const void *func;
   void (*launch)(const KArgs &, int blocks, int threads, size_t smem, void *stream);
 };
@@ -54,7 +56,14 @@ int strict_selftest_division(const double *d_divisors, int n_div, int mode, int 
                              unsigned long long seed, int span, unsigned long long *d_mismatches,
                              void *stream);
 
-const Variant *fast_variants(int *n);
+// variant tables, one per translation unit (kernel family)
+const Variant *fast_lean_variants(int *n);
+const Variant *fast_lean_nc_variants(int *n);
+const Variant *fast_lean_nc_lo_variants(int *n);
+const Variant *fast_bf_variants(int *n);
+const Variant *fast_bf_nc_lo_variants(int *n);
+const Variant *fast_bf6_variants(int *n);
 const Variant *strict_variants(int *n);
+const Variant *strict_bf_variants(int *n);
 
 }  // namespace xlb

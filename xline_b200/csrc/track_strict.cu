@@ -2,6 +2,8 @@
 // operation order (XLB_STRICT 1) so results are IEEE-identical to the NumPy path wherever
 // only + - * / sqrt are involved.  Parity instrument, not the performance path.
 #define XLB_STRICT 1
+#define XLB_NOCHI 0
+#define XLB_MAXORDER 0
 #ifndef XLB_BEAMFIELDS
 #define XLB_BEAMFIELDS 0
 #endif

@@ -30,6 +30,8 @@ T_BEAMBEAM4D, T_SPACECHARGE, T_BEAMBEAM6D = 16, 17, 18
 F_STRICT = 1
 F_BEAMFIELDS = 2
 F_BB6D = 4
+F_LOW_ORDER = 8  # every multipole-family record has order <= LOW_ORDER_MAX (straight-line Horner kernels)
+LOW_ORDER_MAX = 3
 
 DEFAULT_CHUNK_WORDS = 2048  # 16 KiB per TMA bulk copy, 3 in flight per CTA
 MONITOR_FIELDS = ("x", "px", "y", "py", "zeta", "delta", "at_turn")
@@ -572,6 +574,10 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             flags |= F_BB6D
         if tag in (T_BEAMBEAM4D, T_SPACECHARGE) or (tag == T_BEAMBEAM6D and not split):
             flags |= F_BEAMFIELDS
+    horner_orders = [(int(r[0]) >> 8) & 0xFF for tag, r in recs
+                     if tag in (T_MULTIPOLE, T_MULTIPOLE_CURVED) or (tag & 0xC0) == T_THIN_BLOCK]
+    if all(o <= LOW_ORDER_MAX for o in horner_orders):
+        flags |= F_LOW_ORDER
     biggest = max([len(r) for _, r in recs] + [0])
     while biggest + 2 > chunk_words:
         chunk_words *= 2

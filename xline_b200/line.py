@@ -13,7 +13,7 @@ import torch
 
 from . import _cabi
 from . import elements as E
-from .lattice import MONITOR_FIELDS, algorithmic_ops, element_specs, pack_line
+from .lattice import F_LOW_ORDER, MONITOR_FIELDS, algorithmic_ops, element_specs, pack_line
 
 _thick = (E.Drift, E.DriftExact)
 deg2rad = np.pi / 180.0
@@ -322,7 +322,7 @@ class Line(E.Element):
     # ------------------------------------------------------------------ the hot path
     def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
               threads_per_block=0, timed=False, turns_per_item=0, _trace=None, _count_turns=True,
-              _element_offset=0):
+              _element_offset=0, _general_kernels=False):
         """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
         times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
         returns ``None`` like the reference.
@@ -342,6 +342,8 @@ class Line(E.Element):
             if n == 0 or num_turns == 0:
                 return None
             lat = packed.c_lattice(words.data_ptr())
+            if _general_kernels:  # test hook: the unspecialised kernel family (chi column, any order)
+                lat.flags &= ~F_LOW_ORDER
             cols = {}
             for k, t in p._columns():
                 if not t.is_contiguous():
@@ -352,6 +354,17 @@ class Line(E.Element):
             cp.n = n
             for k, t in cols.items():
                 setattr(cp, k, t.data_ptr())
+            # one species (chi == 1 throughout, the reference's default) is the fast case of the C ABI:
+            # no chi column is handed over and the kernels without a chi register run (4 particles per
+            # thread).  The answer is cached on the tensor's storage and version counter, so an in-place
+            # edit of p.chi is seen on the next call.
+            chi = cols.get("chi")
+            if chi is not None:
+                ckey = (chi.data_ptr(), chi._version, n)
+                if getattr(p, "_chi_key", None) != ckey:
+                    p._chi_key, p._chi_trivial = ckey, bool((chi == 1.0).all())
+                if p._chi_trivial and not _general_kernels:
+                    cp.chi = None
             cp.q0, cp.mass0, cp.p0c = p.q0, p.mass0, p.p0c
             cp.beta0, cp.gamma0, cp.energy0 = p.beta0, p.gamma0, p.energy0
             # tallies and monitor storage belong to one state of the line on one device: a line that
