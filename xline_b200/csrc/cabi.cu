@@ -362,32 +362,54 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   need.chi = p->chi != nullptr;
   need.trace = o->trace != nullptr;
   need.max_order = (lat->flags & XLB_F_LOW_ORDER) ? 3 : 255;
-  int ppt_req = o->particles_per_thread;
-  if (ppt_req <= 0) {
-    if (beamfields) ppt_req = 2;
-    else if (strict || need.chi) ppt_req = 3;
-    else ppt_req = 4;
-    // a small beam is spread over all SMs first: fewer particles per thread while the CTAs of the
-    // preferred shape would leave SMs without work (strong scaling, C1)
-    if (!beamfields && o->threads_per_block <= 0) {
-      int dev0 = 0, sms0 = 148;
-      cudaGetDevice(&dev0);
-      cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
-      while (ppt_req > 1 && p->n < static_cast<long long>(ppt_req) * 128 * 3 * sms0) --ppt_req;
-    }
-  }
-  const int threads_req = o->threads_per_block > 0 ? o->threads_per_block : (beamfields && ppt_req < 3 ? 256 : 128);
   const bool trace = need.trace;
   if (trace && (o->num_turns != 1 || o->trace_particles < 1))
     return fail(XLB_EINVAL, "element-by-element trace needs num_turns == 1 and trace_particles >= 1");
   if (split && (trace || strict))
     return fail(XLB_EINVAL, "segmented lattices are for the fast kernels without trace");
-  const Variant *v = pick_variant(need, ppt_req, threads_req);
-  if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
-  int threads = trace ? v->threads
-                      : (o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req));
-  if (threads % 32 || threads > v->threads)
-    return fail(XLB_EINVAL, "threads_per_block must be a multiple of 32 and <= the variant's limit");
+  int dev = 0, sms = 0;
+  XLB_CUDA(cudaGetDevice(&dev));
+  XLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t chunk_bytes = static_cast<size_t>(lat->chunk_words) * 8;
+  const size_t smem = XLB_STAGES * chunk_bytes + (2 * XLB_STAGES + 2) * sizeof(unsigned long long);
+  // The launch shape is chosen per launch from the number of particles still in the beam: a small
+  // (or scraped-down) beam is spread over all SMs first -- fewer particles per thread as long as
+  // the CTAs of the preferred shape would leave CTA slots empty (strong scaling, C1, the heavy-loss
+  // C2 beam).  All variants give the same bits, so the choice is invisible in the results.
+  struct Shape {
+    const Variant *v;
+    int threads, resident, regs;
+  };
+  auto choose = [&](long long n_now, Shape *out) -> int {
+    int ppt_req = o->particles_per_thread;
+    if (ppt_req <= 0) {
+      if (beamfields) ppt_req = 2;
+      else if (strict || need.chi) ppt_req = 3;
+      else ppt_req = 4;
+      if (!beamfields && o->threads_per_block <= 0)
+        while (ppt_req > 1 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) --ppt_req;
+    }
+    const int threads_req =
+        o->threads_per_block > 0 ? o->threads_per_block : (beamfields && ppt_req < 3 ? 256 : 128);
+    const Variant *v = pick_variant(need, ppt_req, threads_req);
+    if (!v) return fail(XLB_EINVAL, "no kernel variant compiled for this lattice");
+    const int threads =
+        trace ? v->threads : (o->threads_per_block > 0 ? o->threads_per_block : std::min(v->threads, threads_req));
+    if (threads % 32 || threads > v->threads)
+      return fail(XLB_EINVAL, "threads_per_block must be a multiple of 32 and <= the variant's limit");
+    XLB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaFuncAttributes fa;
+    XLB_CUDA(cudaFuncGetAttributes(&fa, v->func));
+    int occ = 1;
+    XLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, threads, smem));
+    out->v = v;
+    out->threads = threads;
+    out->resident = std::max(1, occ) * sms;  // CTAs the device holds at once
+    out->regs = fa.numRegs;
+    return XLB_OK;
+  };
+  Shape shape;
+  if ((rc = choose(p->n, &shape)) != XLB_OK) return rc;  // also validates the caller's request
 
   Scratch *s = nullptr;
   if ((rc = get_scratch(&s)) != XLB_OK) return rc;
@@ -400,13 +422,6 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       if (cudaEventRecord(s->done, st) == cudaSuccess) s->have_done = true;
     }
   } done_mark{s, st};
-
-  const size_t chunk_bytes = static_cast<size_t>(lat->chunk_words) * 8;
-  const size_t smem = XLB_STAGES * chunk_bytes + (2 * XLB_STAGES + 2) * sizeof(unsigned long long);
-  XLB_CUDA(cudaFuncSetAttribute(v->func, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
-  cudaFuncAttributes fa;
-  XLB_CUDA(cudaFuncGetAttributes(&fa, v->func));
 
   KArgs a;
   memset(&a, 0, sizeof(a));
@@ -429,12 +444,6 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.elem_off = static_cast<int>(o->element_index_offset);
   const int count_turns = (o->flags & XLB_OPT_NO_TURN_COUNT) ? 0 : 1;
 
-  int occ = 1;
-  XLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->func, threads, smem));
-  int dev = 0, sms = 0;
-  XLB_CUDA(cudaGetDevice(&dev));
-  XLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int resident = std::max(1, occ) * sms;  // CTAs the device holds at once
   const int tpi = (o->turns_per_item == 0) ? 5 : o->turns_per_item;
   // 0 = automatic: long jobs are cut into launches of 100 turns so that survivors get
   // re-compacted now and then; < 0 = one launch whatever the length
@@ -485,6 +494,9 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     a.num_turns = turns;
     a.n = n_active;
     a.idx = idx;
+    if ((rc = choose(n_active, &shape)) != XLB_OK) return rc;
+    const Variant *v = shape.v;
+    const int threads = shape.threads, resident = shape.resident;
     const long long per_block = static_cast<long long>(threads) * v->ppt;
     const int blocks = static_cast<int>((n_active + per_block - 1) / per_block);
     int grid = blocks;
@@ -576,7 +588,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
     else if (!(s->sched_rate >= 0.0)) s->sched_rate = 0.0;
   }
   g_stats.kernel_ms = total_ms;
-  g_stats.regs_per_thread = fa.numRegs;
+  g_stats.regs_per_thread = shape.regs;
   g_stats.smem_bytes = static_cast<int>(smem);
   g_stats.n_alive_in = p->n;
   g_stats.n_alive_out = n_active;
