@@ -408,10 +408,11 @@ def run_extras(ctx, args, which):
         r, _ = measure(ctx, line, factory(cols, p0c, m0), 400, 1, 5,
                        "C5: PS Booster + 120 SCQGaussProfile kicks + BeamMonitor, 1M particles x 400 turns "
                        "(full size 1e6 x 1e4: scripts/run_c5_psb.py)")
-        # the convention counts a wofz call as 100 operations; the Weideman evaluation spends ~400
+        # the convention counts a wofz call as 100 operations; the Weideman evaluation (synthetic
+        # division by a real quadratic: 38 x 2 FMA + set-up and remainder) spends ~190
         nsc = sum(1 for e in line.elements if type(e).__name__.startswith("SC"))
         r["roofline"]["executed_flops_estimate_per_particle_turn"] = r["roofline"][
-            "algorithmic_fp64_ops_per_particle_turn"] + nsc * 2 * 300
+            "algorithmic_fp64_ops_per_particle_turn"] + nsc * 2 * 90
         out["c5"] = r
     return out
 
@@ -565,9 +566,9 @@ def run_b200(args):
             "traffic": traffic,
             "peak_source": "measured: xlb_measure_fp64_peak (8 independent DFMA chains/thread), same process; "
                            "MEASURED_PEAKS.json has no FP64 entry; peak_nominal = 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz",
-            "hbm_view": {"bytes_per_launch_algorithmic": 196 * n * max(1, -(-args.turns_per_launch // 5)),
+            "hbm_view": {"bytes_per_launch_algorithmic": 188 * n * max(1, -(-args.turns_per_launch // 5)),
                          "note": "particle state is register-resident inside a work item; per particle and 5-turn "
-                                 "item 92 B are loaded and 104 B stored"},
+                                 "item 84 B are loaded and 104 B stored (one species: no chi column)"},
             "ncu": ncu_note,
         })
 

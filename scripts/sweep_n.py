@@ -17,7 +17,7 @@ turns = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 rows = []
 for n in (10_000, 30_000, 62_500, 100_000, 125_000, 150_000, 200_000, 300_000, 500_000, 1_000_000):
     line, cols, p0c, m0 = configs.config_lhc(n)
-    for ppt, thr in ((0, 0), (3, 128), (2, 128), (2, 256), (1, 128), (1, 256)):
+    for ppt, thr in ((0, 0), (4, 128), (3, 128), (2, 128), (2, 256), (1, 128), (1, 256)):
         best = 0.0
         for rep in range(2):
             p = xl.Particles(p0c=p0c, mass0=m0, **cols)

@@ -5,7 +5,7 @@
   is bit-identical to the NumPy path except for sin() in the 12 cavities) after 1, 10, 100
   and 1000 turns on 20 000 particles, per amplitude bin.
 
-Writes profiles/accuracy_r1.json.
+Writes profiles/accuracy_<tag>.json (tag = first argument, default r2).
 """
 import json
 import os
@@ -112,7 +112,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     for d in ("profiles", "gpurun_out"):  # gpurun_out/ is what travels back from the GPU box
         os.makedirs(os.path.join(ROOT, d), exist_ok=True)
-        with open(os.path.join(ROOT, d, "accuracy_r1.json"), "w") as fh:
+        with open(os.path.join(ROOT, d, "accuracy_%s.json" % (sys.argv[1] if len(sys.argv) > 1 else "r2")), "w") as fh:
             json.dump(res, fh, indent=1)
 
 

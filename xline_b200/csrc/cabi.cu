@@ -387,7 +387,9 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       else if (strict || need.chi) ppt_req = 3;
       else ppt_req = 4;
       if (!beamfields && o->threads_per_block <= 0)
-        while (ppt_req > 1 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) --ppt_req;
+        // (not below 2: one particle per thread doubles the warps but also the per-record
+        // instructions issued, and loses at every beam size -- profiles/r2_sweep_n.json)
+        while (ppt_req > 2 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) --ppt_req;
     }
     const int threads_req =
         o->threads_per_block > 0 ? o->threads_per_block : (beamfields && ppt_req < 3 ? 256 : 128);
