@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define XLB_ABI_VERSION 3
+#define XLB_ABI_VERSION 4
 
 /* error codes */
 #define XLB_OK 0
@@ -49,20 +49,30 @@ extern "C" {
  * words (chunk_words even, chunk = unit of one TMA bulk copy into shared memory).  A
  * chunk is a sequence of records; a record starts on an even word (16 B aligned):
  *
- *   word 0  header  = tag (8 bits) | aux << 8 (8 bits) | size << 16 (16 bits, record length
- *                     in 16-byte pairs) | (uint64)element_index << 32
+ *   word 0  header  = tag (8 bits) | aux << 8 (8 bits) | size << 16 (14 bits, record length
+ *                     in 16-byte pairs) | XLB_HDR_* flags (bits 30, 31) |
+ *                     (uint64)element_index << 32
  *   word 1  first fp64 parameter (or padding)
  *   word 2..        further parameters, record padded to an even number of words
  *
  * Records never straddle a chunk; every chunk ends with an XLB_T_END_CHUNK record and
  * the last chunk ends with XLB_T_END_TURN instead.  Parameter layout per tag is
- * documented next to the tag.  `element_index` is the position in the reference's
+ * documented next to the tag.
+ *
+ * Path length.  `s` advances by the drift lengths only (elements.py:56,72), by the same
+ * amount for every particle that stays in the beam.  The fast kernels therefore do no
+ * arithmetic on it in the element maps: word 1 of an END_TURN record is the length of the
+ * pass it closes (the whole lattice, or one segment of a segmented lattice), added once per
+ * pass; and every record at which a particle can be lost (the three LIMIT_* tags and the
+ * block records) carries `s_here`, the drift lengths from the start of the pass up to the
+ * record, added for the particles it removes.  The strict kernels ignore both and keep the
+ * reference's per-particle sequential sum.  `element_index` is the position in the reference's
  * `Line.elements` list (what `at_element` reports).  Two encodings exist, selected by
  * XLB_F_STRICT: "fast" (constants pre-folded for FMA-friendly evaluation) and "strict"
  * (raw reference parameters, evaluated in the reference's operation order).
  * --------------------------------------------------------------------------------- */
 enum xlb_tag {
-  XLB_T_END_TURN = 0,       /* no parameters                                          */
+  XLB_T_END_TURN = 0,       /* [hdr,length of the pass that ends here]                */
   XLB_T_END_CHUNK = 1,      /* no parameters                                          */
   XLB_T_DRIFT = 2,          /* [hdr,length]                      elements.py:48-56    */
   XLB_T_DRIFT_EXACT = 3,    /* [hdr,length]                      elements.py:64-72    */
@@ -77,9 +87,9 @@ enum xlb_tag {
   XLB_T_SROTATION = 9,      /* [hdr,cos][sin,0]                  elements.py:379-390  */
   XLB_T_DIPOLE_EDGE = 10,   /* [hdr,r21][r43,0]                  elements.py:538-548  */
   XLB_T_LIMIT_RECT = 11,    /* aux=1: symmetric box (fast encoding only);
-                               [hdr,min_x][max_x,min_y][max_y,0] elements.py:401-420  */
-  XLB_T_LIMIT_ELLIPSE = 12, /* [hdr,a*a][b*b,1/(a*a)][1/(b*b),0] elements.py:429-442  */
-  XLB_T_LIMIT_RECT_ELLIPSE = 13, /* [hdr,max_x][max_y,a*a][b*b,1/(a*a)][1/(b*b),0]
+                               [hdr,min_x][max_x,min_y][max_y,s_here] elements.py:401-420 */
+  XLB_T_LIMIT_ELLIPSE = 12, /* [hdr,a*a][b*b,1/(a*a)][1/(b*b),s_here] elements.py:429-442 */
+  XLB_T_LIMIT_RECT_ELLIPSE = 13, /* [hdr,max_x][max_y,a*a][b*b,1/(a*a)][1/(b*b),s_here]
                                                                  elements.py:453-474  */
   XLB_T_MONITOR = 14,       /* [hdr,0][i64 start,i64 skip][i64 num_stores,i64 min_id]
                                [i64 max_id,i64 rolling][i64 data_offset,0]
@@ -94,8 +104,8 @@ enum xlb_tag {
      has bit 7 set and describes the block: bits 0-1 aperture kind (0 none, 1 symmetric
      rect, 2 rect, 3 ellipse), bit 2 curved multipole, bit 3 drift present, bit 4 that drift
      is a DriftExact.  aux=order;
-     [hdr,drift_length][i64 aperture_element_index,0] (kn_i,ks_i) i=order..0
-     [hxl,hyl][length,1/length] if curved
+     [hdr,drift_length][i64 aperture_element_index,s_here] (kn_i,ks_i) i=order..0
+     [hxl,hyl][length,1/length] if curved (header bit XLB_HDR_HX_ONLY: hyl == 0, fast encoding)
      [min_x,max_x][min_y,max_y] (rect) or [a*a,b*b][1/(a*a),1/(b*b)] (ellipse)            */
   XLB_T_THIN_BLOCK = 0x80,
   /* Merged block (fast encoding only): two co-located thin multipoles K1, K2 evaluated as ONE
@@ -105,12 +115,23 @@ enum xlb_tag {
      [hdr,drift_length][i64 a1_index | a2_index << 32, i64 k1_order | has_a1 << 8]
      merged (kn_i,ks_i) i=order..0  [hxl,hyl][length,1/length][knl0,ksl0 of K2] if curved
      [a*a,b*b][1/(a*a),1/(b*b)] if has_a1 (A1 is an ellipse)  A2 limits as above
-     K1's own (kn_i,ks_i) i=k1_order..0 (re-evaluated only for particles lost at A1)        */
+     K1's own (kn_i,ks_i) i=k1_order..0 (re-evaluated only for particles lost at A1)
+     [s_here,0]                                                                            */
   XLB_T_MERGED_BLOCK = 0xA0,
   /* Dipole edge followed by a drift: tag = 0xC0 | drift << 3 | exact << 4;
      [hdr,drift_length][r21,r43]                              elements.py:538-548, 48-72   */
   XLB_T_EDGE_BLOCK = 0xC0
 };
+
+/* Header bit 31, fast encoding, curved block records only: the multipole's hyl is exactly 0 (a
+   horizontal bend).  The kernel then leaves the hyl terms of elements.py:139-154 out -- exact
+   zeros for every finite y -- which saves 6 of the 14 FP64 instructions of the curved kick.
+   Optional: a packer that never sets it gets the general formula.                          */
+#define XLB_HDR_HX_ONLY 0x80000000u
+/* Header bit 30, merged block records: the block has an aperture A1 between its two kicks (the
+   same fact as bit 8 of the record's second i64; the header copy is warp-uniform in the kernel).
+   Mandatory on merged blocks with an A1.                                                    */
+#define XLB_HDR_HAS_A1 0x40000000u
 
 typedef struct xlb_lattice {
   const uint64_t *words; /* n_chunks * chunk_words words                                */

@@ -221,6 +221,27 @@ def _gauss_field(f64, i64, w, x, y, strict):
     return np.where(x < 0, -ex, ex), np.where(y < 0, -ey, ey), npairs
 
 
+def _path_length_words(tag, aux, w, f64, i64):
+    """-> (index of the record's s_here word or None, by how much the record advances s)."""
+    if tag in (T_DRIFT, T_DRIFT_EXACT):
+        return None, f64[w + 1]
+    if tag in (T_LIMIT_RECT, T_LIMIT_ELLIPSE):
+        return w + 5, 0.0
+    if tag == T_LIMIT_RECT_ELLIPSE:
+        return w + 7, 0.0
+    if (tag & 0xC0) == 0xC0:  # dipole edge -> [drift]
+        return None, (f64[w + 1] if tag & 8 else 0.0)
+    if (tag & 0xC0) == 0x80:
+        adv = f64[w + 1] if tag & 8 else 0.0
+        if not tag & 0x20:
+            return w + 3, adv
+        info = int(i64[w + 3])
+        k1_order, has_a1 = info & 0xFF, (info >> 8) & 1
+        t = 2 + aux + 1 + (3 if tag & 4 else 0) + (2 if has_a1 else 0) + (2 if tag & 3 else 0)
+        return w + 2 * (t + k1_order + 1), adv
+    return None, 0.0
+
+
 def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
     """Interpret ``packed`` (a PackedLattice without segments) for ``num_turns`` turns.
     ``monitor``: fp64 array of ``packed.monitor_words`` words (NaN-filled by the caller), the
@@ -235,13 +256,15 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
     for turn in range(num_turns):
         p = _Live(beam)
         done = False
+        s_pass = 0.0  # drift lengths since the start of the pass, summed in record order
         for ch in range(packed.n_chunks):
             if done:
                 break
             w = ch * cw
             while True:
                 hdr = int(words[w])
-                tag, aux, size, elem = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0xFFFF, hdr >> 32
+                tag, aux, size, elem = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0x3FFF, hdr >> 32
+                hx_only = bool((hdr >> 31) & 1)  # XLB_HDR_HX_ONLY
                 assert w % 2 == 0 and w + 2 * size <= (ch + 1) * cw, "record straddles a chunk"
                 p0 = f64[w + 1]
                 pair = lambda m, _w=w: f64[_w + 2 * m: _w + 2 * m + 2]  # noqa: E731
@@ -249,8 +272,17 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                 if tag == T_END_CHUNK:
                     break
                 if tag == T_END_TURN:
+                    assert p0 == s_pass, "END_TURN must carry the length of the pass"
                     done = True
                     break
+                # the path-length bookkeeping of the format (include/xline_b200.h, "Path length")
+                s_at, adv = _path_length_words(tag, aux, w, f64, i64)
+                if s_at is not None:
+                    assert f64[s_at] == s_pass, "s_here of record at word %d" % w
+                if hx_only:
+                    assert (tag & 0xC4) == 0x84 and not strict
+                    assert f64[w + 2 * (2 + aux + 1) + 1] == 0.0, "XLB_HDR_HX_ONLY needs hyl == 0"
+                s_pass = s_pass + adv
                 if len(p) == 0:
                     w = nxt
                     continue
@@ -275,6 +307,7 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                         idxs, info = int(i64[w + 2]), int(i64[w + 3])
                         a1_idx, a2_idx = idxs & 0xFFFFFFFF, idxs >> 32
                         k1_order, has_a1 = info & 0xFF, (info >> 8) & 1
+                        assert has_a1 == (hdr >> 30) & 1, "XLB_HDR_HAS_A1 must mirror the record"
                         curved = k0 = None
                         if tag & 4:
                             curved = (pair(t)[0], pair(t)[1], pair(t + 1)[0], pair(t + 1)[1])

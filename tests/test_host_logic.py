@@ -97,7 +97,7 @@ def _walk(packed):
         pos = c * packed.chunk_words
         while True:
             hdr = int(w[pos])
-            tag, aux, size, idx = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0xFFFF, hdr >> 32
+            tag, aux, size, idx = hdr & 0xFF, (hdr >> 8) & 0xFF, (hdr >> 16) & 0x3FFF, hdr >> 32
             if tag in (lattice.T_END_CHUNK, lattice.T_END_TURN):
                 break
             out.append((tag, aux, idx))
@@ -147,7 +147,7 @@ def test_pack_fuses_multipole_aperture_drift():
     w = pk.words
     f = pk.words.view(np.float64)
     assert f[1] == 3.0 and int(w[2]) == 1  # drift length, aperture element index
-    size0 = (int(w[0]) >> 16) & 0xFFFF
+    size0 = (int(w[0]) >> 16) & 0x3FFF
     assert f[2 * size0 + 1] == 4.0
     line.fuse_records = False
     assert len(_walk(line.pack())) == 8
@@ -189,7 +189,7 @@ def test_cabi_exports_every_declared_symbol():
     L = _cabi.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.xlb_abi_version() == _cabi.ABI_VERSION == 3
+    assert L.xlb_abi_version() == _cabi.ABI_VERSION == 4
     # argument validation happens before any CUDA call
     assert L.xlb_track_device(None, None, None, None) == -1
     assert b"null" in L.xlb_last_error()

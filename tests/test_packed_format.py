@@ -88,7 +88,7 @@ def test_fast_lhc_lattice_uses_every_block_family():
         w = ch * packed.chunk_words
         while True:
             hdr = int(words[w])
-            tag, size = hdr & 0xFF, (hdr >> 16) & 0xFFFF
+            tag, size = hdr & 0xFF, (hdr >> 16) & 0x3FFF
             if tag in (PI.T_END_CHUNK, PI.T_END_TURN):
                 break
             tags.add(tag)

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxline_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPT_NO_TURN_COUNT = 1  # xlb_track_options_t::flags
 
 EXPORTS = (

@@ -534,8 +534,12 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       g_stats.blocks = blocks;
       g_stats.threads = threads;
     } else {
-    if (tpi > 0 && turns > tpi && blocks > resident) {
-      // persistent CTAs + device-side work queue: (block, turn segment) items, segment-major
+    if (tpi > 0 && turns > tpi && blocks > sms) {
+      // persistent CTAs + device-side work queue: (block, turn segment) items, segment-major.
+      // Also when every CTA is resident at once (sms < blocks <= resident): SMs then hold
+      // different numbers of CTAs, a CTA on a fuller SM runs slower, and with one item per CTA
+      // the launch lasts as long as its slowest CTA; with the queue a CTA on a lighter SM takes
+      // over later turn segments of other blocks (C2 at 125 k particles: +10 %).
       const long long segs = (turns + tpi - 1) / tpi;
       if (static_cast<long long>(blocks) * segs < 0xffffffffLL) {
         if ((rc = ensure_queue(s, static_cast<size_t>(blocks) + 1)) != XLB_OK) return rc;
@@ -543,7 +547,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
         a.queue = s->queue;
         a.n_items = static_cast<unsigned int>(blocks * segs);
         a.turns_per_item = tpi;
-        grid = resident;
+        grid = std::min(blocks, resident);
       }
     }
     v->launch(a, grid, threads, smem, st);
@@ -680,7 +684,9 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
       const uint64_t hdr = w[pos];
       const int tag = static_cast<int>(hdr & 0xff);
       const int aux = static_cast<int>((hdr >> 8) & 0xff);
-      const int pairs = static_cast<int>((hdr >> 16) & 0xffff);
+      const int pairs = static_cast<int>((hdr >> 16) & 0x3fff);
+      const bool hdr_a1 = (hdr & XLB_HDR_HAS_A1) != 0;
+      const bool hx_only = ((hdr >> 31) & 1) != 0;  // XLB_HDR_HX_ONLY
       int want = -1;  // expected record length in pairs, -1 = variable
       switch (tag) {
         case XLB_T_END_TURN:
@@ -740,14 +746,26 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
           if ((tag & 0xe0) == XLB_T_MERGED_BLOCK) {
             if (lat->flags & XLB_F_STRICT) return fail(XLB_ELATTICE, "merged block in a strict lattice");
             const int64_t f = static_cast<int64_t>(w[pos + 3]);
+            if ((((f >> 8) & 1) != 0) != hdr_a1)
+              return fail(XLB_ELATTICE, "merged block: XLB_HDR_HAS_A1 disagrees with the record");
             want = 2 + aux + 1 + ((tag & 4) ? 3 : 0) + (((f >> 8) & 1) ? 2 : 0) + ((tag & 3) ? 2 : 0) +
-                   static_cast<int>(f & 0xff) + 1;
+                   static_cast<int>(f & 0xff) + 1 + 1;  // ... K1's pairs, [path length, 0]
             break;
           }
           char buf[96];
           snprintf(buf, sizeof buf, "unknown tag %d in chunk %d at word %d", tag, c, pos);
           return fail(XLB_ELATTICE, buf);
         }
+      }
+      if (hdr_a1 && (tag & 0xe0) != XLB_T_MERGED_BLOCK)
+        return fail(XLB_ELATTICE, "XLB_HDR_HAS_A1 on a record that is not a merged block");
+      if (hx_only) {  // only on curved block records of the fast encoding, and only when hyl == 0
+        const bool block = (tag & 0xc0) == XLB_T_THIN_BLOCK && (tag & 4);
+        if (!block || (lat->flags & XLB_F_STRICT))
+          return fail(XLB_ELATTICE, "XLB_HDR_HX_ONLY on a record that is not a curved block of the fast encoding");
+        double hyl;
+        memcpy(&hyl, &w[pos + 2 * (2 + aux + 1) + 1], sizeof hyl);
+        if (hyl != 0.0) return fail(XLB_ELATTICE, "XLB_HDR_HX_ONLY set but hyl != 0");
       }
       if (lens_chunk[c] && tag != XLB_T_BEAMBEAM6D && tag != XLB_T_END_TURN)
         return fail(XLB_ELATTICE, "a 6D-lens segment holds exactly one BEAMBEAM6D record");

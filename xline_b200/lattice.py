@@ -47,10 +47,15 @@ def _i2u(i):
     return np.array([i], dtype=np.int64).view(np.uint64)[0]
 
 
-def _hdr(tag, aux, idx, size_pairs=1):
+HDR_HX_ONLY = 1 << 31  # header flag: curved block record with hyl == 0 (fast encoding)
+HDR_HAS_A1 = 1 << 30   # header flag: merged block with an aperture between its two kicks
+
+
+def _hdr(tag, aux, idx, size_pairs=1, flags=0):
     assert 0 <= tag < 256 and 0 <= aux < 256 and 0 <= idx < (1 << 31)
-    assert 1 <= size_pairs < (1 << 16), "record too large for the 16-bit size field"
-    return np.uint64(tag | (aux << 8) | (size_pairs << 16) | (idx << 32))
+    assert 1 <= size_pairs < (1 << 14), "record too large for the 14-bit size field"
+    assert flags & ~(HDR_HX_ONLY | HDR_HAS_A1) == 0
+    return np.uint64(tag | (aux << 8) | (size_pairs << 16) | flags | (idx << 32))
 
 
 class _Rec:
@@ -59,6 +64,16 @@ class _Rec:
     def __init__(self, tag, aux, idx, first=0.0):
         self.tag, self.aux, self.idx = tag, aux, idx
         self.w = [np.uint64(0), _f2u(first)]
+        self.flags = 0         # header flag bits (HDR_HX_ONLY)
+        self.drift_len = 0.0   # by how much the record advances s
+        self.s_word = None     # index of the word that receives the path length up to the record
+
+    def path_length_here(self):
+        """Reserve the next word for the path length from the start of the pass to this record
+        (filled in by pack_line): what a particle lost here has travelled."""
+        self.s_word = len(self.w)
+        self.w.append(_f2u(0.0))
+        return self
 
     def f(self, *vals):
         self.w.extend(_f2u(float(v)) for v in vals)
@@ -71,7 +86,7 @@ class _Rec:
     def words(self):
         if len(self.w) & 1:
             self.w.append(np.uint64(0))
-        self.w[0] = _hdr(self.tag, self.aux, self.idx, len(self.w) // 2)
+        self.w[0] = _hdr(self.tag, self.aux, self.idx, len(self.w) // 2, self.flags)
         return self.w
 
 
@@ -256,9 +271,13 @@ def _is_noop(el, name):
 def _pack_element(el, idx, strict, monitors):
     name = type(el).__name__
     if name == "Drift":
-        return _Rec(T_DRIFT, 0, idx, el.length)
+        rec = _Rec(T_DRIFT, 0, idx, el.length)
+        rec.drift_len = float(el.length)
+        return rec
     if name == "DriftExact":
-        return _Rec(T_DRIFT_EXACT, 0, idx, el.length)
+        rec = _Rec(T_DRIFT_EXACT, 0, idx, el.length)
+        rec.drift_len = float(el.length)
+        return rec
     if name == "Multipole":
         order = el.order
         knl, ksl = _pad(el.knl, order + 1), _pad(el.ksl, order + 1)
@@ -301,13 +320,13 @@ def _pack_element(el, idx, strict, monitors):
         return _Rec(T_DIPOLE_EDGE, 0, idx, r21).f(r43, 0.0)
     if name == "LimitRect":
         sym = (not strict) and el.min_x == -el.max_x and el.min_y == -el.max_y
-        return _Rec(T_LIMIT_RECT, 1 if sym else 0, idx, el.min_x).f(el.max_x, el.min_y).f(el.max_y, 0.0)
+        return _Rec(T_LIMIT_RECT, 1 if sym else 0, idx, el.min_x).f(el.max_x, el.min_y).f(el.max_y).path_length_here()
     if name == "LimitEllipse":
         a2, b2 = el.a * el.a, el.b * el.b
-        return _Rec(T_LIMIT_ELLIPSE, 0, idx, a2).f(b2, 1.0 / a2).f(1.0 / b2, 0.0)
+        return _Rec(T_LIMIT_ELLIPSE, 0, idx, a2).f(b2, 1.0 / a2).f(1.0 / b2).path_length_here()
     if name == "LimitRectEllipse":
         a2, b2 = el.a * el.a, el.b * el.b
-        return _Rec(T_LIMIT_RECT_ELLIPSE, 0, idx, el.max_x).f(el.max_y, a2).f(b2, 1.0 / a2).f(1.0 / b2, 0.0)
+        return _Rec(T_LIMIT_RECT_ELLIPSE, 0, idx, el.max_x).f(el.max_y, a2).f(b2, 1.0 / a2).f(1.0 / b2).path_length_here()
     if name == "BeamMonitor":
         assert el.is_turn_ordered  # xline/elements.py:504
         nn = el.max_particle_id - el.min_particle_id + 1 if el.max_particle_id >= el.min_particle_id else 0
@@ -419,7 +438,10 @@ def _pack_thin_block(mp, idx, aper, drift, strict):
         if type(drift[1]).__name__ == "DriftExact":
             tag |= TB_DRIFT_EXACT
     rec = _Rec(tag, order, idx, drift[1].length if drift is not None else 0.0)
-    rec.i(aper_idx, 0)
+    rec.drift_len = float(drift[1].length) if drift is not None else 0.0
+    if curved and mp.hyl == 0 and not strict:
+        rec.flags |= HDR_HX_ONLY
+    rec.i(aper_idx).path_length_here()
     for i in range(order, -1, -1):
         if strict:
             rec.f(knl[i], ksl[i])
@@ -464,7 +486,12 @@ def _pack_merged_block(k1, idx1, a1, k2, idx2, a2, drift):
         if type(drift[1]).__name__ == "DriftExact":
             tag |= TB_DRIFT_EXACT
     rec = _Rec(tag, order, idx2, drift[1].length if drift is not None else 0.0)
+    rec.drift_len = float(drift[1].length) if drift is not None else 0.0
+    if curved and k2.hyl == 0:
+        rec.flags |= HDR_HX_ONLY
     a1_idx = a1[0] if a1 is not None else 0
+    if a1 is not None:
+        rec.flags |= HDR_HAS_A1
     rec.i(a1_idx | (a2_idx << 32), k1.order | ((1 if a1 is not None else 0) << 8))
     for i in range(order, -1, -1):
         rec.f(kn[i] / _FACT[i], ks[i] / _FACT[i])
@@ -479,7 +506,7 @@ def _pack_merged_block(k1, idx1, a1, k2, idx2, a2, drift):
     k1n, k1s = _pad(k1.knl, k1.order + 1), _pad(k1.ksl, k1.order + 1)
     for i in range(k1.order, -1, -1):
         rec.f(k1n[i] / _FACT[i], k1s[i] / _FACT[i])
-    return rec
+    return rec.path_length_here()
 
 
 def _try_merge(live, pos):
@@ -546,8 +573,9 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             rec = _Rec(T_EDGE_BLOCK | TB_DRIFT | (TB_DRIFT_EXACT if type(d).__name__ == "DriftExact" else 0),
                        0, idx, d.length)
             rec.w.extend([plain.w[1], plain.w[2]])  # r21, r43 as evaluated for the plain record
+            rec.drift_len = float(d.length)
             counts[rec.tag] = counts.get(rec.tag, 0) + 1
-            recs.append((rec.tag, rec.words()))
+            recs.append((rec.tag, rec.words(), rec.s_word, rec.drift_len))
             continue
         merged = _try_merge(live, pos - 1) if (fuse and merge and not strict and name == "Multipole") else None
         if merged is not None:
@@ -567,18 +595,18 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             rec = _pack_element(el, idx, strict, monitors)
         tag = rec.tag
         counts[tag] = counts.get(tag, 0) + 1
-        recs.append((tag, rec.words()))
-    split = bool(split_lenses) and not strict and any(t == T_BEAMBEAM6D for t, _ in recs)
-    for tag, _ in recs:
+        recs.append((tag, rec.words(), rec.s_word, rec.drift_len))
+    split = bool(split_lenses) and not strict and any(r[0] == T_BEAMBEAM6D for r in recs)
+    for tag, _, _, _ in recs:
         if tag == T_BEAMBEAM6D:
             flags |= F_BB6D
         if tag in (T_BEAMBEAM4D, T_SPACECHARGE) or (tag == T_BEAMBEAM6D and not split):
             flags |= F_BEAMFIELDS
-    horner_orders = [(int(r[0]) >> 8) & 0xFF for tag, r in recs
+    horner_orders = [(int(r[0]) >> 8) & 0xFF for tag, r, _, _ in recs
                      if tag in (T_MULTIPOLE, T_MULTIPOLE_CURVED) or (tag & 0xC0) == T_THIN_BLOCK]
     if all(o <= LOW_ORDER_MAX for o in horner_orders):
         flags |= F_LOW_ORDER
-    biggest = max([len(r) for _, r in recs] + [0])
+    biggest = max([len(r[1]) for r in recs] + [0])
     while biggest + 2 > chunk_words:
         chunk_words *= 2
     if chunk_words * 8 > 96 * 1024:
@@ -586,25 +614,33 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
     chunks = []    # (words, is last chunk of its segment)
     segments = []  # [first_chunk, n_chunks, kind]
 
-    def close_segment(cur, first, kind):
-        cur += [_hdr(T_END_TURN, 0, 0), np.uint64(0)]
+    # Path length: `s` advances by the drift lengths only (xline/elements.py:56,72).  The fast
+    # kernels do not add them up particle by particle: every END_TURN record carries the length
+    # of the pass (segment) it closes, and every record a particle can be lost at carries the
+    # length from the start of the pass up to itself (see include/xline_b200.h).
+    def close_segment(cur, first, kind, length):
+        cur += [_hdr(T_END_TURN, 0, 0), _f2u(length)]
         chunks.append((cur, True))
         segments.append([first, len(chunks) - first, kind])
 
-    cur, first = [], 0
-    for tag, r in recs:
+    cur, first, s_pass = [], 0, 0.0
+    for tag, r, s_word, drift_len in recs:
         if split and tag == T_BEAMBEAM6D:
             if cur or len(chunks) > first:  # a tracking segment precedes the lens
-                close_segment(cur, first, SEG_MAIN)
-            close_segment(list(r), len(chunks), SEG_BB6D)
-            cur, first = [], len(chunks)
+                close_segment(cur, first, SEG_MAIN, s_pass)
+            close_segment(list(r), len(chunks), SEG_BB6D, 0.0)
+            cur, first, s_pass = [], len(chunks), 0.0
             continue
         if len(cur) + len(r) + 2 > chunk_words:
             cur += [_hdr(T_END_CHUNK, 0, 0), np.uint64(0)]
             chunks.append((cur, False))
             cur = []
+        if s_word is not None:
+            r = list(r)
+            r[s_word] = _f2u(s_pass)
         cur = cur + r
-    close_segment(cur, first, SEG_MAIN)  # the closing tracking segment (may be empty) counts the turn
+        s_pass = s_pass + drift_len
+    close_segment(cur, first, SEG_MAIN, s_pass)  # the closing tracking segment (may be empty) counts the turn
     words = np.zeros(len(chunks) * chunk_words, dtype=np.uint64)
     for i, (ch, last) in enumerate(chunks):
         words[i * chunk_words: i * chunk_words + len(ch)] = np.array(ch, dtype=np.uint64)
