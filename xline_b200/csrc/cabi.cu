@@ -136,7 +136,7 @@ struct Scratch {
   int *block_sums = nullptr;  // compaction scratch
   long long cap = 0;          // capacity of idx (entries)
   int nblocks_cap = 0;
-  unsigned int *queue = nullptr;   // work queue of the persistent kernel: head + per-block progress
+  unsigned int *queue = nullptr;   // work queue of the persistent kernel: two counters + ring of ready items
   size_t queue_cap = 0;
   unsigned int *n_lost = nullptr;  // device counter
   int *n_active = nullptr;         // device survivor count
@@ -386,10 +386,14 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       if (beamfields) ppt_req = 2;
       else if (strict || need.chi) ppt_req = 3;
       else ppt_req = 4;
-      if (!beamfields && o->threads_per_block <= 0)
-        // (not below 2: one particle per thread doubles the warps but also the per-record
-        // instructions issued, and loses at every beam size -- profiles/r2_sweep_n.json)
+      if (!beamfields && o->threads_per_block <= 0) {
+        // (below 2 only for beams that cannot give every SM one 128-thread CTA: one particle per
+        // thread doubles the warps but also the per-record instructions issued, and loses on the
+        // C2 lattice from 30 000 particles on -- profiles/r2_sweep_n.json; C1's 10 000 particles
+        // on 79 CTAs instead of 40: 3.3e9 against 2.3e9 particle-turns/s)
         while (ppt_req > 2 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) --ppt_req;
+        if (ppt_req == 2 && n_now < 128LL * sms) ppt_req = 1;
+      }
     }
     const int threads_req =
         o->threads_per_block > 0 ? o->threads_per_block : (beamfields && ppt_req < 3 ? 256 : 128);
@@ -541,13 +545,22 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       // the launch lasts as long as its slowest CTA; with the queue a CTA on a lighter SM takes
       // over later turn segments of other blocks (C2 at 125 k particles: +10 %).
       const long long segs = (turns + tpi - 1) / tpi;
-      if (static_cast<long long>(blocks) * segs < 0xffffffffLL) {
-        if ((rc = ensure_queue(s, static_cast<size_t>(blocks) + 1)) != XLB_OK) return rc;
-        XLB_CUDA(cudaMemsetAsync(s->queue, 0, (static_cast<size_t>(blocks) + 1) * sizeof(unsigned int), st));
+      if (static_cast<long long>(blocks) * segs < (1LL << 26)) {  // ring of at most 512 MiB
+        // two counters + one 64-bit ready entry per item beyond the first segment of every block
+        const size_t qwords = 2 + 2 * static_cast<size_t>(blocks) * static_cast<size_t>(segs - 1);
+        if ((rc = ensure_queue(s, qwords)) != XLB_OK) return rc;
+        XLB_CUDA(cudaMemsetAsync(s->queue, 0, qwords * sizeof(unsigned int), st));
         a.queue = s->queue;
         a.n_items = static_cast<unsigned int>(blocks * segs);
         a.turns_per_item = tpi;
-        grid = std::min(blocks, resident);
+        // Fewer CTAs than blocks, always: the blocks beyond the grid wait in the ring, whose FIFO
+        // order then rotates the blocks over the CTAs, and all of them advance at the average
+        // speed.  (With every block resident on a CTA of its own a finishing CTA finds only its
+        // own block in the ring -- a static assignment, as slow as the CTAs of the fullest SMs:
+        // C2 at 125 k particles 1.9e7 against 2.2e7.)  Preferably the same number of CTAs on every
+        // SM; when that would idle more than 15 % of the CTAs, a backlog of 1/16 of the blocks.
+        const int q = std::min(blocks, resident), rem = q % sms;
+        grid = (rem * 100 <= q * 15) ? q - rem : q - std::max(1, q / 16);
       }
     }
     v->launch(a, grid, threads, smem, st);

@@ -24,8 +24,9 @@ struct KArgs {
   double *mon;
   long long mon_words;
   unsigned int *n_lost;  // device counter, incremented per lost particle
-  // work queue (nullptr = one item per CTA): [0] = next item, [1 + b] = segments published
-  // for particle block b.  n_items = n_blocks * ceil(num_turns / turns_per_item).
+  // work queue (nullptr = one item per CTA): [0] = next ticket, [1] = entries written, then a ring
+  // of 64-bit READY entries (valid << 63 | segment << 32 | block) for the tickets beyond the first
+  // n_blocks; zeroed before every launch.  n_items = n_blocks * ceil(num_turns / turns_per_item).
   unsigned int *queue;
   unsigned int n_blocks, n_items;
   int turns_per_item;
