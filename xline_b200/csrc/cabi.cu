@@ -441,6 +441,7 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.at_turn = reinterpret_cast<long long *>(p->at_turn);
   a.pid = reinterpret_cast<const long long *>(p->particle_id);
   a.q0 = p->q0; a.p0c = p->p0c; a.beta0 = p->beta0; a.energy0 = p->energy0;
+  a.sc_common = p->q0 * p->q0 * (1.0 - p->beta0 * p->beta0) / (p->p0c * p->beta0);
   a.loss_tally = reinterpret_cast<long long *>(o->loss_tally);
   a.mon = o->monitor_data;
   a.mon_words = o->monitor_words;

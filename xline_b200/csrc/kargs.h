@@ -20,6 +20,9 @@ struct KArgs {
   long long *state, *at_element, *at_turn;
   const long long *pid;
   double q0, p0c, beta0, energy0;
+  // q0^2 (1 - beta0^2) / (p0c beta0): the particle-independent factor of every space-charge kick
+  // (be_beamfields/spacecharge.py:38-40), evaluated once per call on the host
+  double sc_common;
   long long *loss_tally;
   double *mon;
   long long mon_words;
