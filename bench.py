@@ -25,7 +25,8 @@ Printed JSON (one line, rank 0): the contract keys plus
                     pinned host buffers, copies inside the timed region;
   ``configs``       short measurements of the other BASELINE configurations with their own
                     roofline fraction and clocks (c1 FODO incl. the host entry point, c2_heavy_loss =
-                    the SURVEY 8(d) beam, c3 LHC + beam-beam, c4 PETRA IV, c5 PS Booster + space charge);
+                    the SURVEY 8(d) beam, c2_125k = one rank's share of C2 under strong scaling at 8
+                    GPUs, c3 LHC + beam-beam, c4 PETRA IV, c5 PS Booster + space charge);
   ``clocks``, ``gpu_launches``.
 """
 import argparse
@@ -61,7 +62,7 @@ def parse_args():
     ap.add_argument("--cpu-particles", type=int, default=5000, help="CPU sample: particles per process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strict leg and the other configurations")
-    ap.add_argument("--extras", default="strict,c1,c2_heavy_loss,c3,c4,c5")
+    ap.add_argument("--extras", default="strict,c1,c2_heavy_loss,c2_125k,c3,c4,c5")
     return ap.parse_args()
 
 
@@ -382,6 +383,15 @@ def run_extras(ctx, args, which):
                        "survivor-weighted", track_kw=dict(turns_per_launch=args.turns_per_launch))
         out["c2_heavy_loss"] = r
 
+    if "c2_125k" in which and world == 1:
+        # strong-scaling regime on one GPU: the share of one rank when the 1 M particles of C2 are
+        # divided over 8 GPUs (no data-path collective: 8 x this value is what 8 ranks deliver)
+        line, cols, p0c, m0 = configs.config_lhc(125_000)
+        r, _ = measure(ctx, line, factory(cols, p0c, m0), args.turns_per_step, 3, 5,
+                       "C2 lattice, 125 000 particles (1/8 of C2: one rank's share under strong scaling at 8 GPUs)",
+                       track_kw=dict(turns_per_launch=args.turns_per_launch))
+        out["c2_125k"] = r
+
     if "c3" in which and world == 1:
         line, cols, p0c, m0 = configs.config_lhc_beambeam(4_000_000)
         r, _ = measure(ctx, line, factory(cols, p0c, m0), 20, 1, 1,
@@ -409,10 +419,17 @@ def run_extras(ctx, args, which):
                        "C5: PS Booster + 120 SCQGaussProfile kicks + BeamMonitor, 1M particles x 400 turns "
                        "(full size 1e6 x 1e4: scripts/run_c5_psb.py)")
         # the convention counts a wofz call as 100 operations; the Weideman evaluation (synthetic
-        # division by a real quadratic: 38 x 2 FMA + set-up and remainder) spends ~190
+        # division by a real quadratic: 34 x 2 FMA + set-up and remainder) spends ~170
         nsc = sum(1 for e in line.elements if type(e).__name__.startswith("SC"))
         r["roofline"]["executed_flops_estimate_per_particle_turn"] = r["roofline"][
-            "algorithmic_fp64_ops_per_particle_turn"] + nsc * 2 * 90
+            "algorithmic_fp64_ops_per_particle_turn"] + nsc * 2 * 70
+        r["roofline"]["frac_executed_flops_estimate"] = (
+            r["roofline"]["frac"] * r["roofline"]["executed_flops_estimate_per_particle_turn"]
+            / r["roofline"]["algorithmic_fp64_ops_per_particle_turn"])
+        prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as fh:
+                r["roofline"]["ncu"] = json.load(fh).get("c5")
         out["c5"] = r
     return out
 

@@ -86,7 +86,10 @@ enum xlb_tag {
   XLB_T_XYSHIFT = 8,        /* [hdr,dx][dy,0]                    elements.py:274-276  */
   XLB_T_SROTATION = 9,      /* [hdr,cos][sin,0]                  elements.py:379-390  */
   XLB_T_DIPOLE_EDGE = 10,   /* [hdr,r21][r43,0]                  elements.py:538-548  */
-  XLB_T_LIMIT_RECT = 11,    /* aux=1: symmetric box (fast encoding only);
+  /* The three LIMIT_* records may carry the drift that follows the aperture (pack-time
+     peephole Limit* -> Drift): aux bit 4 (XLB_AUX_DRIFT), bit 5 = it is a DriftExact; the drift
+     length follows the record's own pairs as [length,0].                                     */
+  XLB_T_LIMIT_RECT = 11,    /* aux bit 0: symmetric box (fast encoding only);
                                [hdr,min_x][max_x,min_y][max_y,s_here] elements.py:401-420 */
   XLB_T_LIMIT_ELLIPSE = 12, /* [hdr,a*a][b*b,1/(a*a)][1/(b*b),s_here] elements.py:429-442 */
   XLB_T_LIMIT_RECT_ELLIPSE = 13, /* [hdr,max_x][max_y,a*a][b*b,1/(a*a)][1/(b*b),s_here]
@@ -96,8 +99,9 @@ enum xlb_tag {
                                                                  elements.py:485-527  */
   XLB_T_SAWTOOTH_CAVITY = 15, /* as CAVITY                       elements.py:257-263  */
   XLB_T_BEAMBEAM4D = 16,    /* see xline_b200/lattice.py         beambeam.py:45-82    */
-  XLB_T_SPACECHARGE = 17,   /* aux=profile kind (0 coasting,1 q-Gaussian,2 linear
-                               interp,3 cubic spline)            spacecharge.py       */
+  XLB_T_SPACECHARGE = 17,   /* aux bits 0-3 = profile kind (0 coasting,1 q-Gaussian,2 linear
+                               interp,3 cubic spline); aux bit 4/5: the kick is followed by
+                               a Drift / DriftExact of length word 1  spacecharge.py  */
   XLB_T_BEAMBEAM6D = 18,    /* [hdr,(double)n_slices] ...        BB6D.py:15-155       */
   XLB_T__COUNT = 19,
   /* Fused thin multipole -> [aperture] -> [drift] records (pack-time peephole).  The tag
@@ -128,6 +132,9 @@ enum xlb_tag {
    zeros for every finite y -- which saves 6 of the 14 FP64 instructions of the curved kick.
    Optional: a packer that never sets it gets the general formula.                          */
 #define XLB_HDR_HX_ONLY 0x80000000u
+/* aux bits of the LIMIT_* and SPACECHARGE records: a drift fused into the record              */
+#define XLB_AUX_DRIFT 0x10
+#define XLB_AUX_DRIFT_EXACT 0x20
 /* Header bit 30, merged block records: the block has an aperture A1 between its two kicks (the
    same fact as bit 8 of the record's second i64; the header copy is warp-uniform in the kernel).
    Mandatory on merged blocks with an A1.                                                    */

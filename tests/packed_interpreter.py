@@ -226,9 +226,11 @@ def _path_length_words(tag, aux, w, f64, i64):
     if tag in (T_DRIFT, T_DRIFT_EXACT):
         return None, f64[w + 1]
     if tag in (T_LIMIT_RECT, T_LIMIT_ELLIPSE):
-        return w + 5, 0.0
+        return w + 5, (f64[w + 6] if aux & 0x10 else 0.0)
     if tag == T_LIMIT_RECT_ELLIPSE:
-        return w + 7, 0.0
+        return w + 7, (f64[w + 8] if aux & 0x10 else 0.0)
+    if tag == T_SPACECHARGE:
+        return None, (f64[w + 1] if aux & 0x10 else 0.0)
     if (tag & 0xC0) == 0xC0:  # dipole edge -> [drift]
         return None, (f64[w + 1] if tag & 8 else 0.0)
     if (tag & 0xC0) == 0x80:
@@ -374,16 +376,22 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                     p.py = p.py + pair(1)[0] * p.y
                 elif tag == T_LIMIT_RECT:
                     lim = np.array([p0, pair(1)[0], pair(1)[1], pair(2)[0]])
-                    p.lose(~_inside(AP_RECT_SYM if aux else AP_RECT, p.x, p.y, lim, strict), elem, turn)
+                    p.lose(~_inside(AP_RECT_SYM if aux & 1 else AP_RECT, p.x, p.y, lim, strict), elem, turn)
+                    if aux & 0x10:  # the drift that follows the aperture
+                        (_drift_exact if aux & 0x20 else _drift)(p, pair(3)[0])
                 elif tag == T_LIMIT_ELLIPSE:
                     lim = np.array([p0, pair(1)[0], pair(1)[1], pair(2)[0]])
                     p.lose(~_inside(AP_ELLIPSE, p.x, p.y, lim, strict), elem, turn)
+                    if aux & 0x10:
+                        (_drift_exact if aux & 0x20 else _drift)(p, pair(3)[0])
                 elif tag == T_LIMIT_RECT_ELLIPSE:
                     mx, my = p0, pair(1)[0]
                     lim = np.array([pair(1)[1], pair(2)[0], pair(2)[1], pair(3)[0]])
                     inside = ((p.x >= -mx) & (p.x <= mx) & (p.y >= -my) & (p.y <= my)
                               & _inside(AP_ELLIPSE, p.x, p.y, lim, strict))
                     p.lose(~inside, elem, turn)
+                    if aux & 0x10:
+                        (_drift_exact if aux & 0x20 else _drift)(p, pair(4)[0])
                 elif tag == T_RFMULTIPOLE:  # [hdr,V][k,lag] then per order [knl,ksl][pn,ps]
                     k, lag = pair(1)
                     ktau = k * (p.zeta / p.rvv / beam.beta0)
@@ -433,18 +441,19 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                     t = w + 2 * (2 + nf)  # first word after the field block
                     base, p1 = f64[t], f64[t + 1]
                     common = beam.q0 * beam.q0 * (1.0 - beam.beta0 * beam.beta0) / (beam.p0c * beam.beta0) * base
+                    kind = aux & 0xF
                     lam = 1.0
-                    if aux == 1:  # q-Gaussian in zeta / rvv: [sqrt_beta/cq, 1-q][1/(1-q), 0][i64 gauss, 0]
+                    if kind == 1:  # q-Gaussian in zeta / rvv: [sqrt_beta/cq, 1-q][1/(1-q), 0][i64 gauss, 0]
                         arg = p1 * (p.zeta / p.rvv) ** 2
                         if int(i64[t + 6]):
                             lam = f64[t + 2] * np.exp(-arg)
                         else:
                             up = np.maximum(1.0 + (-arg) * f64[t + 3], 0.0)
                             lam = f64[t + 2] * up ** f64[t + 4]
-                    elif aux in (2, 3):  # [base,z0][dz,0][i64 n,0] then the profile / the spline
+                    elif kind in (2, 3):  # [base,z0][dz,0][i64 n,0] then the profile / the spline
                         z0, dz, npts = p1, f64[t + 2], int(i64[t + 4])
                         i = np.clip(np.floor((p.zeta - z0) / dz).astype(np.int64), 0, npts - 2)
-                        if aux == 2:
+                        if kind == 2:
                             prof = f64[t + 6: t + 6 + npts]
                             xi = z0 + i * dz
                             lam = (prof[i + 1] - prof[i]) / dz * (p.zeta - xi) + prof[i]
@@ -459,6 +468,8 @@ def track(packed, cols, p0c, mass0, num_turns=1, monitor=None):
                     fact = p.chi * p.charge_ratio * common * lam
                     p.px = p.px + fact * ex
                     p.py = p.py + fact * ey
+                    if aux & 0x10:  # the drift that follows the kick
+                        (_drift_exact if aux & 0x20 else _drift)(p, p0)
                 else:
                     raise NotImplementedError("tag 0x%02x is outside the interpreter's scope" % tag)
                 w = nxt

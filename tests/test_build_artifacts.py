@@ -85,7 +85,11 @@ def test_four_particle_kernel_does_not_spill_inside_the_record_loop():
             and top_lo <= int(re.search(r"\bBRA\b.*?(0x[0-9a-f]+)", ln).group(1), 16) <= top_hi]
     assert back
     loop_end = max(back)
-    inside = [i for i in spills if redux[0] - 12 <= i <= loop_end]
+    # top of the record loop = the earliest back-edge target (a few instructions above the decode)
+    first_target = min(int(re.search(r"\bBRA\b.*?(0x[0-9a-f]+)", lines[i]).group(1), 16) for i in back)
+    loop_top = min(i for i, ln in enumerate(lines) if addr(ln) >= first_target)
+    assert redux[0] - 12 <= loop_top <= redux[0]
+    inside = [i for i in spills if loop_top <= i <= loop_end]
     assert not inside, [lines[i] for i in inside[:5]]
 
 

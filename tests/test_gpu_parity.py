@@ -1002,3 +1002,103 @@ def test_element_track_loop_is_one_pass_of_the_line():
         assert np.array_equal(gb["state"], ga["state"])
     assert np.array_equal(gc["at_element"], ga["at_element"])
     assert int(gc["at_turn"].max()) == 0
+
+
+@pytest.mark.parametrize("config", ["lhc", "petra4"])
+@pytest.mark.parametrize("with_chi", [False, True])
+def test_horizontal_bend_flag_changes_no_bit(config, with_chi):
+    """XLB_HDR_HX_ONLY (curved block records with hyl == 0: the hyl terms of elements.py:139-154
+    are left out) against the same lattice packed without the flag (general formula): every
+    column bit for bit, with and without a chi column (one-species and general kernel family)."""
+    from xline_b200 import configs
+
+    n = 30_000
+    line, cols, p0c, m0 = (configs.config_lhc if config == "lhc" else configs.config_petra4)(n)
+    cols = dict(cols)
+    if with_chi:
+        cols["chi"] = 1.0 + 0.01 * np.random.default_rng(3).standard_normal(n)
+    flagged = sum(1 for w in line.pack().words if (int(w) >> 31) & 1 and (int(w) & 0xC4) == 0x84)
+    outs = []
+    for flag in (True, False):
+        line.flag_horizontal_bends = flag
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=2)
+        outs.append(p.to_numpy())
+    line.flag_horizontal_bends = True
+    assert flagged > 100  # (header words only look like this by construction: tag 0x84.., bit 31)
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
+
+
+def test_one_chunk_lattice_resident_in_shared_memory_equals_the_ring():
+    """A lattice that fits one chunk is copied to shared memory once per work item and stays
+    there; packed into many small chunks the same lattice goes through the TMA ring turn by
+    turn.  Same bits, losses included, with and without the work queue."""
+    import xline_b200 as xl
+    from xline_b200 import configs
+
+    line, cols, p0c, m0 = configs.config_fodo(150_000)
+    line = xl.Line(list(line.elements) + [xl.LimitRect(min_x=-3e-3, max_x=3e-3, min_y=-3e-3, max_y=3e-3),
+                                          xl.LimitEllipse(a=3.5e-3, b=3.2e-3)])
+    outs = []
+    for chunk_words, tpi in ((None, -1), (None, 5), (32, -1), (32, 5)):
+        line.chunk_words = chunk_words
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=23, turns_per_item=tpi)
+        assert (line.pack().n_chunks == 1) == (chunk_words is None)
+        outs.append(p.to_numpy())
+    assert 0 < (outs[0]["state"] == 0).sum() < len(outs[0]["x"])
+    for o in outs[1:]:
+        for k in o:
+            if k == "s":
+                assert np.allclose(outs[0][k], o[k], rtol=1e-12, atol=0)
+            else:
+                assert np.array_equal(outs[0][k], o[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_idle_lanes_are_parked_and_never_counted(strict):
+    """Lanes whose particle is gone keep running with their warp, parked at the origin.  Here a
+    fifth of the beam is lost over 30 different turns at four kinds of aperture, dipole kicks move
+    whatever sits at the origin, and one aperture does not contain the origin of its (shifted)
+    frame at all, so lanes parked there wander through the ring and trip apertures again: loss flags, at_element, at_turn and the tallies
+    must still be the oracle's -- every lost particle counted once, nothing else counted."""
+    import xline_b200 as xl
+
+    n, turns = 3000, 60
+    rng = np.random.default_rng(11)
+    els = [
+        xl.Multipole(knl=[3e-5, 0.4], ksl=[-1e-5]), xl.LimitRect(min_x=-4e-3, max_x=4e-3, min_y=-4e-3, max_y=4e-3),
+        xl.Drift(length=1.5),
+        xl.Multipole(knl=[-1e-5, -0.4, 12.0]), xl.LimitEllipse(a=5e-3, b=4.5e-3), xl.Drift(length=1.5),
+        xl.LimitRect(min_x=-3.0e-3, max_x=9e-3, min_y=-9e-3, max_y=9e-3),   # asymmetric box
+        xl.Multipole(knl=[1e-3], hxl=1e-3, length=1.0), xl.LimitRectEllipse(max_x=6e-3, max_y=6e-3, a=7e-3, b=6.5e-3),
+        xl.Drift(length=0.7),
+        # in the shifted frame the box does not contain the origin: a lane parked here is flagged
+        # again and again
+        xl.XYShift(dx=3e-3, dy=0.0), xl.LimitRect(min_x=-6e-3, max_x=-1e-4, min_y=-9e-3, max_y=9e-3),
+        xl.XYShift(dx=-3e-3, dy=0.0),
+    ]
+    line = xl.Line(els)
+    cols = dict(x=rng.normal(0, 1.0e-3, n), px=rng.normal(0, 2e-4, n), y=rng.normal(0, 1.0e-3, n),
+                py=rng.normal(0, 2e-4, n), zeta=rng.normal(0, 0.05, n), delta=rng.normal(0, 3e-4, n))
+    p0c, m0 = 6.5e12, 938.272e6
+    for ppt in (1, 4):
+        line.invalidate()
+        p = make_particles(cols, p0c, m0)
+        line.track(p, num_turns=turns, strict=strict, particles_per_thread=ppt)
+        got = p.to_numpy()
+        ref = H.run_oracle(line.to_specs(), cols, p0c, m0, num_turns=turns)
+        lost = ref["state"] == 0
+        assert 0.15 * n < lost.sum() < n  # a fifth of the beam goes, over many turns
+        assert len(np.unique(ref["at_turn"][lost])) > 15
+        for k in ("state", "at_element", "at_turn"):
+            assert np.array_equal(got[k], ref[k]), k
+        tally = line.loss_tally.cpu().numpy()
+        assert tally.sum() == lost.sum()
+        assert np.array_equal(tally, np.bincount(ref["at_element"][lost], minlength=len(line)))
+        for k in H.COORDS + ("s",):
+            if strict:
+                assert np.array_equal(got[k], ref[k]), k
+            else:
+                assert H.scaled_err(got[k], ref[k]) < 1e-9, k

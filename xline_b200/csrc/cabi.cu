@@ -727,8 +727,8 @@ int xlb_lattice_validate(const xlb_lattice_t *lat) {
         case XLB_T_DIPOLE_EDGE: want = 2; break;
         case XLB_T_RFMULTIPOLE: want = 2 + 2 * (aux + 1); break;
         case XLB_T_LIMIT_RECT:
-        case XLB_T_LIMIT_ELLIPSE: want = 3; break;
-        case XLB_T_LIMIT_RECT_ELLIPSE: want = 4; break;
+        case XLB_T_LIMIT_ELLIPSE: want = 3 + ((aux & XLB_AUX_DRIFT) ? 1 : 0); break;
+        case XLB_T_LIMIT_RECT_ELLIPSE: want = 4 + ((aux & XLB_AUX_DRIFT) ? 1 : 0); break;
         case XLB_T_MONITOR: want = 5; break;
         case XLB_T_BEAMBEAM4D:
         case XLB_T_SPACECHARGE:

@@ -47,6 +47,7 @@ def _i2u(i):
     return np.array([i], dtype=np.int64).view(np.uint64)[0]
 
 
+AUX_DRIFT, AUX_DRIFT_EXACT = 0x10, 0x20  # aux bits of the LIMIT_* and SPACECHARGE records: fused drift
 HDR_HX_ONLY = 1 << 31  # header flag: curved block record with hyl == 0 (fast encoding)
 HDR_HAS_A1 = 1 << 30   # header flag: merged block with an aperture between its two kicks
 
@@ -66,6 +67,7 @@ class _Rec:
         self.w = [np.uint64(0), _f2u(first)]
         self.flags = 0         # header flag bits (HDR_HX_ONLY)
         self.drift_len = 0.0   # by how much the record advances s
+        self.drift_before = 0.0  # part of it that comes BEFORE the point a particle can be lost at
         self.s_word = None     # index of the word that receives the path length up to the record
 
     def path_length_here(self):
@@ -542,7 +544,7 @@ SEG_MAIN, SEG_BB6D = 0, 1
 
 
 def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noops=True, fuse=True,
-              merge=True, split_lenses=True):
+              merge=True, split_lenses=True, hx_only=True):
     """Pack ``elements`` (the ``Line.elements`` list).  ``element_index`` in every record
     is the position in that list, so ``at_element`` matches the reference's indexing even
     though exact no-ops (zero-length drifts, all-zero multipoles, disabled lenses) are not
@@ -551,7 +553,11 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
     ``split_lenses`` (fast encoding only): every BeamBeam6D record gets a chunk of its own
     and the lattice becomes a sequence of segments -- tracking-kernel segments separated by
     6D-lens segments (``xlb_lattice_t::segments``) -- so that the tracking kernels need not
-    carry the register-hungry 6D lens."""
+    carry the register-hungry 6D lens.
+
+    ``hx_only`` (fast encoding only): flag curved block records whose ``hyl`` is exactly zero with
+    ``XLB_HDR_HX_ONLY`` so that the kernel leaves the ``hyl`` terms out (same bits, fewer
+    instructions); ``False`` packs them for the general formula (the tests compare the two)."""
     assert chunk_words % 2 == 0 and chunk_words >= 16
     monitors = dict(layout=[], words=0)
     recs = []
@@ -575,7 +581,30 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             rec.w.extend([plain.w[1], plain.w[2]])  # r21, r43 as evaluated for the plain record
             rec.drift_len = float(d.length)
             counts[rec.tag] = counts.get(rec.tag, 0) + 1
-            recs.append((rec.tag, rec.words(), rec.s_word, rec.drift_len))
+            recs.append((rec.tag, rec.words(), rec.s_word, rec.drift_len, rec.drift_before))
+            continue
+        nxt = type(live[pos][1]).__name__ if pos < len(live) else None
+        if fuse and name in ("LimitRect", "LimitEllipse", "LimitRectEllipse") and nxt in ("Drift", "DriftExact"):
+            # aperture -> drift in one record (aux bit 4; the drift length in a pair of its own)
+            d = live[pos][1]
+            pos += 1
+            rec = _pack_element(el, idx, strict, monitors)
+            rec.aux |= AUX_DRIFT | (AUX_DRIFT_EXACT if nxt == "DriftExact" else 0)
+            rec.f(d.length, 0.0)
+            rec.drift_len = float(d.length)
+            counts[rec.tag] = counts.get(rec.tag, 0) + 1
+            recs.append((rec.tag, rec.words(), rec.s_word, rec.drift_len, rec.drift_before))
+            continue
+        if fuse and name in ("SCCoasting", "SCQGaussProfile", "SCInterpolatedProfile") and nxt in ("Drift", "DriftExact"):
+            # space-charge kick -> drift in one record (aux bit 4; the drift length in word 1)
+            d = live[pos][1]
+            pos += 1
+            rec = _pack_element(el, idx, strict, monitors)
+            rec.aux |= AUX_DRIFT | (AUX_DRIFT_EXACT if nxt == "DriftExact" else 0)
+            rec.w[1] = _f2u(float(d.length))
+            rec.drift_len = float(d.length)
+            counts[rec.tag] = counts.get(rec.tag, 0) + 1
+            recs.append((rec.tag, rec.words(), rec.s_word, rec.drift_len, rec.drift_before))
             continue
         merged = _try_merge(live, pos - 1) if (fuse and merge and not strict and name == "Multipole") else None
         if merged is not None:
@@ -595,14 +624,16 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             rec = _pack_element(el, idx, strict, monitors)
         tag = rec.tag
         counts[tag] = counts.get(tag, 0) + 1
-        recs.append((tag, rec.words(), rec.s_word, rec.drift_len))
+        if not hx_only:
+            rec.flags &= ~HDR_HX_ONLY
+        recs.append((tag, rec.words(), rec.s_word, rec.drift_len, rec.drift_before))
     split = bool(split_lenses) and not strict and any(r[0] == T_BEAMBEAM6D for r in recs)
-    for tag, _, _, _ in recs:
+    for tag, _, _, _, _ in recs:
         if tag == T_BEAMBEAM6D:
             flags |= F_BB6D
         if tag in (T_BEAMBEAM4D, T_SPACECHARGE) or (tag == T_BEAMBEAM6D and not split):
             flags |= F_BEAMFIELDS
-    horner_orders = [(int(r[0]) >> 8) & 0xFF for tag, r, _, _ in recs
+    horner_orders = [(int(r[0]) >> 8) & 0xFF for tag, r, _, _, _ in recs
                      if tag in (T_MULTIPOLE, T_MULTIPOLE_CURVED) or (tag & 0xC0) == T_THIN_BLOCK]
     if all(o <= LOW_ORDER_MAX for o in horner_orders):
         flags |= F_LOW_ORDER
@@ -624,7 +655,7 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
         segments.append([first, len(chunks) - first, kind])
 
     cur, first, s_pass = [], 0, 0.0
-    for tag, r, s_word, drift_len in recs:
+    for tag, r, s_word, drift_len, drift_before in recs:
         if split and tag == T_BEAMBEAM6D:
             if cur or len(chunks) > first:  # a tracking segment precedes the lens
                 close_segment(cur, first, SEG_MAIN, s_pass)
@@ -637,7 +668,7 @@ def pack_line(elements, strict=False, chunk_words=DEFAULT_CHUNK_WORDS, drop_noop
             cur = []
         if s_word is not None:
             r = list(r)
-            r[s_word] = _f2u(s_pass)
+            r[s_word] = _f2u(s_pass + drift_before)
         cur = cur + r
         s_pass = s_pass + drift_len
     close_segment(cur, first, SEG_MAIN, s_pass)  # the closing tracking segment (may be empty) counts the turn

@@ -26,7 +26,7 @@ def _is_thick(element):
 
 class Line(E.Element):
     _base = (("elements", tuple), ("element_names", tuple))
-    _pack_options = ("fuse_records", "chunk_words", "merge_multipoles", "split_lenses")
+    _pack_options = ("fuse_records", "chunk_words", "merge_multipoles", "split_lenses", "flag_horizontal_bends")
 
     def __setattr__(self, name, value):
         # edit tracking (elements.py): the element list and the packing options stamp the line,
@@ -49,6 +49,7 @@ class Line(E.Element):
         self.chunk_words = None   # 8-byte words per TMA chunk (None = lattice.DEFAULT_CHUNK_WORDS)
         self.merge_multipoles = True  # fast encoding: co-located thin multipoles become one kick
         self.split_lenses = True      # fast encoding: BeamBeam6D lenses run as kernels of their own
+        self.flag_horizontal_bends = True  # fast encoding: XLB_HDR_HX_ONLY on curved blocks with hyl == 0
         self._monitor_buf = None
         self._buffers_key = None
         self.loss_tally = None
@@ -296,13 +297,14 @@ class Line(E.Element):
             chunk_words = self.chunk_words
         self._current_stamp()
         key = ("host", bool(strict), chunk_words, self.fuse_records, self.merge_multipoles, self.split_lenses,
-               getattr(self, "_keep_noops", False))
+               self.flag_horizontal_bends, getattr(self, "_keep_noops", False))
         hit = self._cache.get("host_%d" % strict)
         if hit is not None and hit[0] == key:
             return hit[1]
         kw = {} if chunk_words is None else {"chunk_words": chunk_words}
         packed = pack_line(self.elements, strict=strict, fuse=self.fuse_records,
                            merge=self.merge_multipoles, split_lenses=self.split_lenses,
+                           hx_only=self.flag_horizontal_bends,
                            drop_noops=not getattr(self, "_keep_noops", False), **kw)
         lat = packed.c_lattice()
         _cabi.check(_cabi.lib().xlb_lattice_validate(C.byref(lat)))
