@@ -274,15 +274,22 @@ def test_compaction_kernel_matches_numpy():
         assert np.array_equal(idx[: len(want)].cpu().numpy(), want)
 
 
-def test_host_entry_point_matches_device_entry_point():
-    """xlb_track_host (host buffers, copies inside) == Line.track on device tensors."""
+@pytest.mark.parametrize("pinned,n", [(False, 3000), (True, 3000), (True, 40_000)])
+def test_host_entry_point_matches_device_entry_point(pinned, n):
+    """xlb_track_host == Line.track on device tensors: pageable host buffers (copies inside),
+    small pinned buffers (tracked in place through their device aliases, no copies) and pinned
+    buffers above the in-place limit (copies again); apertures so that lost particles are written
+    back through the same path."""
+    import xline_b200 as xl
     from xline_b200 import _cabi, configs
 
-    line, cols, p0c, m0 = configs.config_fodo(3000)
+    line, cols, p0c, m0 = configs.config_fodo(n)
+    line = xl.Line(list(line.elements) + [xl.LimitEllipse(a=3.5e-3, b=3.5e-3)])
     p = make_particles(cols, p0c, m0)
     line.track(p, num_turns=7)
     want = p.to_numpy()
-    hp = make_particles(cols, p0c, m0, device="cpu")
+    assert 0 < (want["state"] == 0).sum() < n
+    hp = xl.Particles(p0c=p0c, mass0=m0, device="cpu", pinned=pinned, **cols)
     packed = line.pack()
     lat = _cabi.Lattice(packed.words.ctypes.data, packed.words.size, packed.chunk_words,
                         packed.n_chunks, packed.n_elements, packed.flags)
