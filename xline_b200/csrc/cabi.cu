@@ -540,11 +540,10 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
       g_stats.threads = threads;
     } else {
     if (tpi > 0 && turns > tpi && blocks > sms) {
-      // persistent CTAs + device-side work queue: (block, turn segment) items, segment-major.
-      // Also when every CTA is resident at once (sms < blocks <= resident): SMs then hold
+      // persistent CTAs + a device-side ring of ready (block, turn segment) items (track_impl.cuh).
+      // Also when every CTA could be resident at once (sms < blocks <= resident): SMs would hold
       // different numbers of CTAs, a CTA on a fuller SM runs slower, and with one item per CTA
-      // the launch lasts as long as its slowest CTA; with the queue a CTA on a lighter SM takes
-      // over later turn segments of other blocks (C2 at 125 k particles: +10 %).
+      // the launch lasts as long as its slowest CTA.
       const long long segs = (turns + tpi - 1) / tpi;
       if (static_cast<long long>(blocks) * segs < (1LL << 26)) {  // ring of at most 512 MiB
         // two counters + one 64-bit ready entry per item beyond the first segment of every block
@@ -554,9 +553,9 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
         a.queue = s->queue;
         a.n_items = static_cast<unsigned int>(blocks * segs);
         a.turns_per_item = tpi;
-        // Fewer CTAs than blocks, always: the blocks beyond the grid wait in the ring, whose FIFO
-        // order then rotates the blocks over the CTAs, and all of them advance at the average
-        // speed.  (With every block resident on a CTA of its own a finishing CTA finds only its
+        // Fewer CTAs than blocks (unless the blocks load every SM equally): the blocks beyond the
+        // grid wait in the ring, whose FIFO
+        // order then rotates the blocks over the CTAs, and all of them advance at the average speed.  (With every block resident on a CTA of its own a finishing CTA finds only its
         // own block in the ring -- a static assignment, as slow as the CTAs of the fullest SMs:
         // C2 at 125 k particles 1.9e7 against 2.2e7.)  Preferably the same number of CTAs on every
         // SM; when that would idle more than 15 % of the CTAs, a backlog of 1/16 of the blocks.
