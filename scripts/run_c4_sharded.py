@@ -53,8 +53,14 @@ def main():
     ev1.record()
     torch.cuda.synchronize(dev)
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    # per-rank device time and work (shard imbalance, if any, shows here)
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+    per_rank[rank, 0] = ms[0]
+    per_rank[rank, 1] = float(int(p.at_turn.sum()))
+    per_rank[rank, 2] = float(int((p.state == 1).sum()))
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank)
     # survival per amplitude band (radial, in units of the grid extent), reduced over ranks
     rr = np.sqrt((x / 6e-3) ** 2 + (y / 3e-3) ** 2)
     band = torch.from_numpy(np.minimum((rr * 10).astype(np.int64), 14)).to(dev)
@@ -72,6 +78,9 @@ def main():
             "device_ms_max_over_ranks": float(ms.item()), "wall_s": time.perf_counter() - t0,
             "particle_turns_per_s": (done - before) / (float(ms.item()) * 1e-3),
             "loss_tally_total": int(line.loss_tally.sum().item()),
+            "per_rank": [{"rank": r, "device_ms": float(per_rank[r, 0]), "particle_turns_incl_warmup": int(per_rank[r, 1]),
+                          "alive": int(per_rank[r, 2])} for r in range(world)],
+            "gpu": torch.cuda.get_device_name(dev),
             "survival_by_amplitude_band": [float(s / t) if t > 0 else None for s, t in zip(surv.tolist(), tot.tolist())],
         }
         line_json = json.dumps(out)
