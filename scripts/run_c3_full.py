@@ -1,6 +1,6 @@
 """BASELINE configuration C3 at full size on one GPU: LHC lattice with 72 BeamBeam4D and
 2 BeamBeam6D (15 slices) lenses (examples/beambeam), 1e7 particles x 1e3 turns.
-Writes gpurun_out/r1_c3_full.json.
+Writes gpurun_out/c3_full.json.
 
     python scripts/run_c3_full.py [n_particles] [n_turns]
 """
@@ -44,4 +44,4 @@ out = dict(config="C3 LHC + 72 BeamBeam4D + 2 BeamBeam6D x 15 slices (examples/b
            segments=line.pack().segments.tolist())
 print(json.dumps(out), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/r1_c3_full.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/c3_full.json", "w"), indent=1)

@@ -1,7 +1,7 @@
 """BASELINE configuration C5 at full size on one GPU: the PS Booster lattice of tests/psb
 (xline_b200.configs.config_psb: 120 SCQGaussProfile kicks, 264 apertures, RF), 1e6 particles x
 1e4 turns, one BeamMonitor storing every 100th turn for the first 1e5 particle ids.
-Writes gpurun_out/r1_c5_psb.json.
+Writes gpurun_out/c5_psb_full.json.
 
     python scripts/run_c5_psb.py [n_particles] [n_turns]
 """
@@ -60,4 +60,4 @@ out = dict(config="C5 PS Booster (tests/psb), 120 SCQGaussProfile kicks, BeamMon
            regs=line.last_stats["regs_per_thread"])
 print(json.dumps(out), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/r1_c5_psb.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/c5_psb_full.json", "w"), indent=1)
