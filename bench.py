@@ -583,9 +583,11 @@ def run_b200(args):
             "traffic": traffic,
             "peak_source": "measured: xlb_measure_fp64_peak (8 independent DFMA chains/thread), same process; "
                            "MEASURED_PEAKS.json has no FP64 entry; peak_nominal = 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz",
-            "hbm_view": {"bytes_per_launch_algorithmic": 188 * n * max(1, -(-args.turns_per_launch // 5)),
-                         "note": "particle state is register-resident inside a work item; per particle and 5-turn "
-                                 "item 84 B are loaded and 104 B stored (one species: no chi column)"},
+            "hbm_view": {"bytes_per_launch_algorithmic": 188 * n * args.turns_per_launch,
+                         "note": "particle state is register-resident inside a work item (one turn of the LHC "
+                                 "lattice: 121 chunks); per particle and item 84 B are loaded and 104 B stored "
+                                 "(one species: no chi column) -- through L2, where the beam (1 M x 120 B) stays "
+                                 "from one item to the next: see ncu.dram_bytes_per_launch"},
             "ncu": ncu_note,
         })
 

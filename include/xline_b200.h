@@ -206,9 +206,10 @@ typedef struct xlb_track_options {
   int64_t monitor_words;     /* capacity of monitor_data in fp64 words                   */
   double compact_threshold;  /* re-compact when lost/active exceeds this (default 1/128) */
   int32_t turns_per_item;    /* granularity of the device-side work queue: a launch of more
-                                turns than this, over more particle blocks than the device
-                                holds at once, runs persistent CTAs that pull (particle block,
-                                turn segment) items.  0 = default (5), < 0 = off          */
+                                turns than this, over more particle blocks than there are SMs,
+                                runs persistent CTAs that pull (particle block, turn segment)
+                                items.  0 = automatic (one turn, or as many as stream 16
+                                lattice chunks), < 0 = off                                */
   int32_t flags;             /* XLB_OPT_* below                                          */
   double *trace;             /* optional element-by-element trace, [n_elements][6][trace_particles]
                                 fp64 (x px y py zeta delta after every element for the first

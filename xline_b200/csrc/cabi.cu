@@ -391,7 +391,9 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
         // thread doubles the warps but also the per-record instructions issued, and loses on the
         // C2 lattice from 30 000 particles on -- profiles/r2_sweep_n.json; C1's 10 000 particles
         // on 79 CTAs instead of 40: 3.3e9 against 2.3e9 particle-turns/s)
-        while (ppt_req > 2 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) --ppt_req;
+        // (three per thread wins nowhere in the closing sweep, profiles/r2c_sweep_n.json: 200 k
+        // particles 2.45e7 with two, 2.38e7 with three, 2.11e7 with four)
+        if (ppt_req > 2 && n_now < static_cast<long long>(ppt_req) * 128 * 3 * sms) ppt_req = 2;
         if (ppt_req == 2 && n_now < 128LL * sms) ppt_req = 1;
       }
     }
@@ -451,7 +453,13 @@ static int track_device_impl(const xlb_lattice_t *lat, xlb_particles_t *p,
   a.elem_off = static_cast<int>(o->element_index_offset);
   const int count_turns = (o->flags & XLB_OPT_NO_TURN_COUNT) ? 0 : 1;
 
-  const int tpi = (o->turns_per_item == 0) ? 5 : o->turns_per_item;
+  // Work-item length.  An item costs a load and a store of its block's particles and a ticket
+  // (microseconds); a shorter item leaves a shorter tail at the end of a launch (the last, partly
+  // filled round of items) and rotates the blocks faster.  Automatic: one turn when a turn streams
+  // 16 chunks or more (LHC: 121, C2 at 250 k particles +3 %, at 1 M +1 % over five turns), else
+  // as many turns as make 16 chunks (PS Booster: 6).
+  const int tpi = (o->turns_per_item == 0) ? std::max(1, (16 + lat->n_chunks - 1) / lat->n_chunks)
+                                           : o->turns_per_item;
   // 0 = automatic: long jobs are cut into launches of 100 turns so that survivors get
   // re-compacted now and then; < 0 = one launch whatever the length
   // (the kernel counts the chunks of a launch in 32 bits: a launch never exceeds 2^31 / n_chunks turns)
