@@ -139,7 +139,8 @@ def test_rfmultipole_and_monitor_records():
 
 def _random_line(rng):
     """A random thin-lens line, biased towards the sequences the packer's peepholes look for
-    (multipole -> aperture -> drift, co-located multipoles, dipole edge -> drift) and towards
+    (multipole -> aperture -> drift, co-located multipoles, dipole edge -> drift, aperture -> drift)
+    and towards
     their edge cases (exact no-ops, zero-length curved multipoles, asymmetric boxes)."""
     import xline_b200 as xl
 
@@ -188,6 +189,8 @@ def _random_line(rng):
             if rng.random() < 0.8:
                 els.append(drift())
         elif u < 0.6:
+            if rng.random() < 0.35:  # a collimator between two drifts: aperture -> drift in one record
+                els.append(aperture())
             els.append(drift())
         elif u < 0.7:
             els.append(xl.DipoleEdge(h=0.01, e1=rng.normal(0, 0.05), hgap=0.02, fint=0.5))
