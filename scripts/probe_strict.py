@@ -13,7 +13,7 @@ from xline_b200 import configs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 turns = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 line, cols, p0c, m0 = configs.config_lhc(n)
-for ppt, thr in ((1, 256), (2, 256), (2, 128), (3, 128)):
+for ppt, thr in ((2, 128), (3, 128), (4, 128)):
     p = xl.Particles(p0c=p0c, mass0=m0, **cols)
     line.track(p, num_turns=1, strict=True, particles_per_thread=ppt, threads_per_block=thr)
     p = xl.Particles(p0c=p0c, mass0=m0, **cols)
