@@ -24,6 +24,16 @@
 #define XLB_MAXORDER 0
 #endif
 
+// Beam-field kernels keep the warps of a CTA in step: one CTA barrier per lattice chunk.  Their
+// hot code (field maps, Faddeeva loop, the thin-lens records in between) is several times the L0
+// instruction cache of an SM sub-partition, and warps that run through the same records at the
+// same time share every fetched line (PS Booster, C5: 2.78e8 -> 3.0e8 particle-turns/s; LHC with
+// 74 lenses and the thin-lens families, whose loop fits the cache: no change -- measured,
+// profiles/r2d_c5_sync_probe.json).
+#if XLB_BEAMFIELDS && !defined(XLB_SYNC_CHUNK)
+#define XLB_SYNC_CHUNK 1
+#endif
+
 #if XLB_BEAMFIELDS == 2
 #define XLB_NS fast_bf6
 #define XLB_FAMILY "/beamfields6d"
@@ -56,6 +66,8 @@ XLB_DEF_TRACE_VARIANT()
 // lattice (74 lenses among 5 500 records on C3), so the register budget is set by them and
 // the rarely executed beam-field code is allowed to spill.
 #define XLB_SHAPES(X) X(1, 256, 2) X(2, 256, 2) X(3, 128, 3)
+#elif XLB_BEAMFIELDS && XLB_NOCHI && defined(XLB_EXP_512)
+#define XLB_SHAPES(X) X(1, 256, 2) X(2, 256, 2) X(2, 512, 1) X(3, 128, 3) X(4, 128, 3)
 #elif XLB_BEAMFIELDS && XLB_NOCHI
 #define XLB_SHAPES(X) X(1, 256, 2) X(2, 256, 2) X(3, 128, 3) X(4, 128, 3)
 #elif XLB_BEAMFIELDS
