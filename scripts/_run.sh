@@ -1,18 +1,17 @@
-# Round-2 closing measurements on one B200 (run under gpurun from the repository root); the
-# artefacts land in gpurun_out/ and are copied to profiles/ by hand.
+# Closing measurements of round 2 after the per-chunk barrier of the beam-field kernels (r2d; run
+# under gpurun from the repository root); artefacts land in gpurun_out/ and are copied to profiles/
+# by hand.  The thin-lens kernels (C2, C4) are the ones of the r2c run: their ncu launch list, DRAM
+# figures, source-level capture, N sweep and accuracy study (profiles/r2c_*) were not repeated;
+# the full r2c command list is in the history of this file.
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1; tail -3 gpurun_out/pytest_final.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-python bench.py > gpurun_out/r2c_bench_n1.json 2> gpurun_out/bench.err || tail -5 gpurun_out/bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2c_bench_reference_arm.json 2>> gpurun_out/bench.err
-# launch list of the bench command (per-launch times are cold-cache and serialised: shares, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2c_ncu_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_l.log 2>&1
-tail -2 gpurun_out/ncu_l.log | cut -c1-300
-# DRAM traffic and pipe figures of one launch of the bench command itself
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__inst_executed_pipe_fp64.sum --clock-control none -k regex:track_kernel -s 8 -c 1 --csv --log-file gpurun_out/r2c_ncu_dram_bench_launch.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_d.log 2>&1
-tail -4 gpurun_out/r2c_ncu_dram_bench_launch.csv | cut -c1-400
-# source-level captures: C2 (one wave of the default kernel, work-queue path) and C5
-ncu --set full --clock-control none --import-source on -k regex:track_kernel -c 1 -f -o gpurun_out/r2c_c2 python scripts/profile_target.py 227328 20 4 c2 > gpurun_out/ncu_c2.log 2>&1; tail -1 gpurun_out/ncu_c2.log
-ncu --set full --clock-control none --import-source on -k regex:track_kernel -c 1 -f -o gpurun_out/r2c_c5 python scripts/profile_target.py 151552 40 2 c5 > gpurun_out/ncu_c5.log 2>&1; tail -1 gpurun_out/ncu_c5.log
-python scripts/sweep_n.py gpurun_out/r2c_sweep_n.json 30 > gpurun_out/sweep.log 2>&1; tail -2 gpurun_out/sweep.log
-python tests/accuracy_study.py r2c > gpurun_out/acc.log 2>&1; tail -3 gpurun_out/acc.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log | cut -c1-200
+python bench.py > gpurun_out/r2d_bench_n1.json 2> gpurun_out/bench.err || tail -5 gpurun_out/bench.err
+cut -c1-300 gpurun_out/r2d_bench_n1.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2d_bench_reference_arm.json 2>> gpurun_out/bench.err
+cut -c1-300 gpurun_out/r2d_bench_reference_arm.json
+# C5 at full size (1e6 particles x 1e4 turns, BeamMonitor), clocks sampled alongside
+nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_throttle_reasons.active --format=csv -lms 500 > gpurun_out/full_clocks.csv 2>/dev/null &
+SMI=$!
+python scripts/run_c5_psb.py > gpurun_out/c5_full.log 2>&1; tail -2 gpurun_out/c5_full.log | cut -c1-300
+kill $SMI

@@ -323,14 +323,16 @@ class Line(E.Element):
 
     # ------------------------------------------------------------------ the hot path
     def track(self, p, num_turns=1, strict=False, turns_per_launch=0, particles_per_thread=0,
-              threads_per_block=0, timed=False, turns_per_item=0, _trace=None, _count_turns=True,
+              threads_per_block=0, timed=False, turns_per_item=0, compact_threshold=0.0, _trace=None,
+              _count_turns=True,
               _element_offset=0, _general_kernels=False):
         """``for el in self.elements: el.track(p)`` (xline/line.py:89-95), ``num_turns``
         times, in one fused kernel launch on ``p``'s GPU.  Mutates ``p`` in place and
         returns ``None`` like the reference.
 
         ``strict=True`` selects the reference-operation-order kernel (parity instrument).
-        ``turns_per_launch`` > 0 splits the job and re-compacts survivors between launches.
+        ``turns_per_launch`` > 0 splits the job and re-compacts survivors between launches
+        (when more than ``compact_threshold`` of the lanes went idle; 0 = the library's 1/128).
         """
         if p.device.type != "cuda":
             raise RuntimeError(
@@ -393,6 +395,7 @@ class Line(E.Element):
             opts.threads_per_block = int(threads_per_block)
             opts.turns_per_launch = int(turns_per_launch)
             opts.turns_per_item = int(turns_per_item)
+            opts.compact_threshold = float(compact_threshold)
             opts.flags = 0 if _count_turns else _cabi.OPT_NO_TURN_COUNT
             opts.element_index_offset = int(_element_offset)
             if _trace is not None:
