@@ -20,6 +20,8 @@ if LIBNAME != "base":
     _cabi.LIB_PATH = os.path.join(ROOT, "xline_b200", "exp", "lib_%s.so" % LIBNAME)
 SHAPE = os.environ.get("XLB_SHAPE", "")  # "2x512": particles per thread x threads per block
 KW = dict(zip(("particles_per_thread", "threads_per_block"), (int(v) for v in SHAPE.split("x")))) if SHAPE else {}
+if os.environ.get("XLB_STRICT"):  # the bit-exact kernels
+    KW["strict"] = True
 
 import xline_b200 as xl  # noqa: E402
 from xline_b200 import configs  # noqa: E402
@@ -53,7 +55,7 @@ def main():
                 best = max(best, int(p.at_turn.sum()) / (st["kernel_ms"] * 1e-3))
             ok = p.state == 1
             chk = float(p.x[ok].double().sum() + p.py[ok].double().sum() + p.zeta[ok].double().sum())
-            row = {"lib": LIBNAME, "shape": SHAPE, "config": cfg, "n": n, "turns": turns, "turns_per_item": tpi, "ptps": best,
+            row = {"lib": LIBNAME, "shape": SHAPE, "strict": bool(KW.get("strict")), "config": cfg, "n": n, "turns": turns, "turns_per_item": tpi, "ptps": best,
                    "n_chunks": line.pack().n_chunks, "chunk_words": line.pack().chunk_words,
                    "blocks": st["blocks"], "threads": st["threads"], "regs": st["regs_per_thread"],
                    "alive": int(ok.sum()), "checksum": repr(chk)}
