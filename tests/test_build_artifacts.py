@@ -108,3 +108,38 @@ def test_sass_has_tma_bulk_copies_and_uniform_header():
     assert "HMMA" not in sass and "UTCHMMA" not in sass  # no tensor cores on this path
     # FP64 is where the arithmetic is: DFMA dominates the FP64-pipe instructions
     assert sass.count("DFMA") > 10 * sass.count("FFMA")
+
+
+def _kernel_sass(obj_name, kernel_key):
+    obj = os.path.join(B.OBJ, obj_name)
+    if not os.path.exists(obj):
+        B.build()
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    return sass, sass.split(kernel_key)[1].split("Function :")[0]
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_beam_field_kernels_keep_their_warps_in_step():
+    """DESIGN.md section 4.2, "Warps in step": the beam-field families carry one CTA barrier per
+    lattice chunk (item fetch, publish, chunk loop: three BAR.SYNC), the thin-lens families do
+    without it (two)."""
+    _, bf = _kernel_sass("track_fast_bf_nc_lo.o", "track_kernelILi2ELi256ELi2ELb0E")
+    _, lean = _kernel_sass("track_fast_nc.o", "track_kernelILi4ELi128ELi3ELb0E")
+    n_bf, n_lean = bf.count("BAR.SYNC"), lean.count("BAR.SYNC")
+    assert n_bf == n_lean + 1, (n_bf, n_lean)
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_faddeeva_loop_is_straight_line_for_two_particles_per_thread():
+    """Up to four chains the Weideman recurrence is unrolled completely: every pair of
+    coefficients is read ONCE (LDCU.128 from the constant bank into uniform registers, the DFMAs
+    take them as operands) -- (N - 2) / 2 loads in the whole kernel, no loop.  Three and four
+    particles per thread (six, eight chains) keep the rolled loop: four iterations per trip."""
+    n_coeff = int(re.search(r"#define XLB_WEID_N (\d+)",
+                            open(os.path.join(B.CSRC, "faddeeva_coeffs.inc")).read()).group(1))
+    loads = {}
+    for ppt, key in ((1, "ILi1ELi256ELi2ELb0E"), (2, "ILi2ELi256ELi2ELb0E"), (3, "ILi3ELi128ELi3ELb0E")):
+        _, body = _kernel_sass("track_fast_bf_nc_lo.o", "track_kernel" + key)
+        loads[ppt] = len(re.findall(r"LDCU\.128 UR\d+, c\[0x3\]", body))
+    assert loads[1] == loads[2] == (n_coeff - 2) // 2, loads
+    assert loads[3] < loads[2], loads
