@@ -133,13 +133,14 @@ def test_beam_field_kernels_keep_their_warps_in_step():
 def test_faddeeva_loop_is_straight_line_for_two_particles_per_thread():
     """Up to four chains the Weideman recurrence is unrolled completely: every pair of
     coefficients is read ONCE (LDCU.128 from the constant bank into uniform registers, the DFMAs
-    take them as operands) -- (N - 2) / 2 loads in the whole kernel, no loop.  Three and four
-    particles per thread (six, eight chains) keep the rolled loop: four iterations per trip."""
+    take them as operands) -- (N - 2) / 2 loads per copy of the field code, no loop; the body is
+    inlined at its two call sites (BeamBeam4D, space charge).  Three and four particles per
+    thread (six, eight chains) keep one out-of-line copy with the rolled loop."""
     n_coeff = int(re.search(r"#define XLB_WEID_N (\d+)",
                             open(os.path.join(B.CSRC, "faddeeva_coeffs.inc")).read()).group(1))
     loads = {}
     for ppt, key in ((1, "ILi1ELi256ELi2ELb0E"), (2, "ILi2ELi256ELi2ELb0E"), (3, "ILi3ELi128ELi3ELb0E")):
         _, body = _kernel_sass("track_fast_bf_nc_lo.o", "track_kernel" + key)
         loads[ppt] = len(re.findall(r"LDCU\.128 UR\d+, c\[0x3\]", body))
-    assert loads[1] == loads[2] == (n_coeff - 2) // 2, loads
+    assert loads[1] == loads[2] == 2 * ((n_coeff - 2) // 2), loads
     assert loads[3] < loads[2], loads
